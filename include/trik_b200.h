@@ -1,0 +1,239 @@
+/*
+ * trik_b200.h -- C ABI of libtrikb200: the B200 drop-in for the per-frame pixel pipeline of
+ * trikset/trik-media-sensors-dsp (webcam object/line sensors, ov7670 object/line/mxn sensors).
+ *
+ * Two surfaces:
+ *
+ *  1. The reference's own codec surface.  Every sensor of the reference exports the SAME two
+ *     symbols, TRIK_VIDTRANSCODE_CV_FXNS and TRIK_VIDTRANSCODE_CV_IALG
+ *     (<sensor>/trik_vidtranscode_cv.h:17-18, <sensor>/src/vidtranscode_cv_fxns.c:36-40,63-65),
+ *     and one DSP server image holds one sensor.  Here one library holds all five, so the tables
+ *     carry the sensor in their name (TRIKB200_<KIND>_FXNS); the five thin alias libraries
+ *     libtrik_vidtranscode_cv_<kind>.so re-export them under the reference's names for a caller
+ *     that links exactly one sensor, as the reference's callers do.
+ *     Signatures, ownership, error codes and bookkeeping follow vidtranscode_cv_fxns.c:85-334
+ *     line by line (see DESIGN.md section "Boundary" for the table).
+ *
+ *  2. A batch extension (new, additive).  process() rejects numBufs != 1
+ *     (vidtranscode_cv_fxns.c:199-204), so many frames per call need a new entry point:
+ *     trikb200_processBatch().  Its results are defined as those of n sequential process()
+ *     calls on the same handle, including the per-handle state the reference carries between
+ *     calls (ov7670 line sensor: m_hStart/m_hStop lag one frame; ov7670 object sensor: the HSV
+ *     range persists while setHsvRange == 0).
+ *
+ * Plain pointers and sizes only: no CUDA or torch types in any signature.  A "device pointer"
+ * is a raw CUDA device address; a "stream" is a cudaStream_t passed as void* (NULL = the
+ * handle's own stream).
+ */
+#ifndef TRIK_B200_H_
+#define TRIK_B200_H_
+
+#include "trik_xdm.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- image formats: <sensor>/trik_vidtranscode_cv.h:20-32 --------------------------------- */
+typedef enum TRIK_VIDTRANSCODE_CV_VideoFormat {
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_UNKNOWN = 0,
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_RGB888 = XDM_CUSTOMENUMBASE,
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_RGB565,
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_RGB565X,
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV444,
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422,   /* webcam sensors: interleaved Y0 U Y1 V */
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P,  /* ov7670 sensors: luma plane + interleaved chroma plane */
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_RGB888HSV,
+    TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_METABITMAP
+} TRIK_VIDTRANSCODE_CV_VideoFormat;
+
+/* ---- create-time and run-time parameters: <sensor>/trik_vidtranscode_cv.h:35-48 ------------ */
+typedef struct TRIK_VIDTRANSCODE_CV_Params {
+    IVIDTRANSCODE_Params base;
+} TRIK_VIDTRANSCODE_CV_Params;
+
+typedef struct TRIK_VIDTRANSCODE_CV_DynamicParams {
+    IVIDTRANSCODE_DynamicParams base;
+    XDAS_Int32 inputHeight;
+    XDAS_Int32 inputWidth;
+    XDAS_Int32 inputLineLength;   /* byte stride of one row; YUV422P: of each plane, chroma plane at inputLineLength*inputHeight */
+    XDAS_Int32 outputLineLength[IVIDTRANSCODE_MAXOUTSTREAMS];
+} TRIK_VIDTRANSCODE_CV_DynamicParams;
+
+/* ---- per-frame arguments --------------------------------------------------------------------
+ * The reference gives every sensor's structs the same names; here the three distinct layouts
+ * get distinct names.  Layouts are byte-identical to the reference's. */
+
+/* webcam object / webcam line / ov7670 line: webcam/line_sensor/trik_vidtranscode_cv.h:48-74 */
+typedef struct TRIKB200_RangeInArgsAlg {
+    XDAS_UInt16 detectHueFrom; /* [0..359] */
+    XDAS_UInt16 detectHueTo;   /* [0..359] */
+    XDAS_UInt8  detectSatFrom; /* [0..100] */
+    XDAS_UInt8  detectSatTo;   /* [0..100] */
+    XDAS_UInt8  detectValFrom; /* [0..100] */
+    XDAS_UInt8  detectValTo;   /* [0..100] */
+    XDAS_Bool   autoDetectHsv;
+} TRIKB200_RangeInArgsAlg;
+
+typedef struct TRIKB200_TargetOutArgsAlg {
+    XDAS_Int8   targetX;    /* [-100..100] */
+    XDAS_Int8   targetY;    /* [-100..100] */
+    XDAS_UInt8  targetSize; /* [0..100] */
+    XDAS_UInt16 detectHue;
+    XDAS_UInt16 detectHueTolerance;
+    XDAS_UInt16 detectSat;
+    XDAS_UInt16 detectSatTolerance;
+    XDAS_UInt16 detectVal;
+    XDAS_UInt16 detectValTolerance;
+} TRIKB200_TargetOutArgsAlg;
+
+/* ov7670 object sensor: ov7670/object_sensor/trik_vidtranscode_cv.h:51-81 */
+typedef struct TRIKB200_ObjInArgsAlg {
+    XDAS_Bool   setHsvRange;
+    XDAS_UInt16 detectHue;     /* [0..359] */
+    XDAS_UInt16 detectHueTol;
+    XDAS_UInt8  detectSat;     /* [0..100] */
+    XDAS_UInt8  detectSatTol;
+    XDAS_UInt8  detectVal;     /* [0..100] */
+    XDAS_UInt8  detectValTol;
+    XDAS_Bool   autoDetectHsv;
+} TRIKB200_ObjInArgsAlg;
+
+typedef struct XDAS_Target {
+    XDAS_Int8  x;    /* [-100..100] */
+    XDAS_Int8  y;    /* [-100..100] */
+    XDAS_UInt8 size; /* [0..100] */
+} XDAS_Target;
+
+typedef struct TRIKB200_ObjOutArgsAlg {
+    XDAS_Target target[8];
+    XDAS_UInt16 detectHue;
+    XDAS_UInt16 detectHueTolerance;
+    XDAS_UInt16 detectSat;
+    XDAS_UInt16 detectSatTolerance;
+    XDAS_UInt16 detectVal;
+    XDAS_UInt16 detectValTolerance;
+} TRIKB200_ObjOutArgsAlg;
+
+/* ov7670 mxn sensor: ov7670/mxn_sensor/trik_vidtranscode_cv.h:49-62 */
+typedef struct TRIKB200_MxnInArgsAlg {
+    XDAS_Int32 widthM;   /* number of cell ROWS (the reference swaps the names, cv_ball_detector_seqpass.hpp:585-586) */
+    XDAS_Int32 heightN;  /* number of cell COLUMNS */
+} TRIKB200_MxnInArgsAlg;
+
+typedef struct TRIKB200_MxnOutArgsAlg {
+    XDAS_Int32 outColor[100]; /* 0x00RRGGBB per cell, row-major; entries past widthM*heightN are left untouched */
+} TRIKB200_MxnOutArgsAlg;
+
+/* full xDM argument blocks (base + alg), as the reference's TRIK_VIDTRANSCODE_CV_InArgs/OutArgs */
+typedef struct { IVIDTRANSCODE_InArgs  base; TRIKB200_RangeInArgsAlg   alg; } TRIKB200_RangeInArgs;
+typedef struct { IVIDTRANSCODE_OutArgs base; TRIKB200_TargetOutArgsAlg alg; } TRIKB200_TargetOutArgs;
+typedef struct { IVIDTRANSCODE_InArgs  base; TRIKB200_ObjInArgsAlg     alg; } TRIKB200_ObjInArgs;
+typedef struct { IVIDTRANSCODE_OutArgs base; TRIKB200_ObjOutArgsAlg    alg; } TRIKB200_ObjOutArgs;
+typedef struct { IVIDTRANSCODE_InArgs  base; TRIKB200_MxnInArgsAlg     alg; } TRIKB200_MxnInArgs;
+typedef struct { IVIDTRANSCODE_OutArgs base; TRIKB200_MxnOutArgsAlg    alg; } TRIKB200_MxnOutArgs;
+
+/* ---- sensor kinds --------------------------------------------------------------------------- */
+typedef enum TRIKB200_Kind {
+    TRIKB200_KIND_WO = 0, /* trik/webcam/object_sensor : YUV422,  Range/Target args */
+    TRIKB200_KIND_WL = 1, /* trik/webcam/line_sensor   : YUV422,  Range/Target args */
+    TRIKB200_KIND_OO = 2, /* trik/ov7670/object_sensor : YUV422P, Obj args          */
+    TRIKB200_KIND_OL = 3, /* trik/ov7670/line_sensor   : YUV422P, Range/Target args */
+    TRIKB200_KIND_OM = 4, /* trik/ov7670/mxn_sensor    : YUV422P, Mxn args          */
+    TRIKB200_KIND_COUNT = 5
+} TRIKB200_Kind;
+
+/* ---- surface 1: the codec function tables ---------------------------------------------------
+ * Replaces TRIK_VIDTRANSCODE_CV_FXNS / TRIK_VIDTRANSCODE_CV_IALG of <sensor>/src/vidtranscode_cv_fxns.c:36-65.
+ *   ialg.algAlloc  (fxns.c:85-102)  2 records: {sizeof(handle), EXTERNAL, PERSIST}, {0x1000, DARAM0, PERSIST}
+ *   ialg.algInit   (fxns.c:146-166) + creates the device buffers and the CUDA stream owned by the handle
+ *   ialg.algFree   (fxns.c:114-136) returns the same two records with base filled
+ *   process        (fxns.c:174-264) one frame, HOST buffers
+ *   control        (fxns.c:272-334) XDM_GETSTATUS/GETBUFINFO/SETPARAMS/RESET/SETDEFAULT/FLUSH/GETVERSION */
+extern IVIDTRANSCODE_Fxns TRIKB200_WO_FXNS;
+extern IVIDTRANSCODE_Fxns TRIKB200_WL_FXNS;
+extern IVIDTRANSCODE_Fxns TRIKB200_OO_FXNS;
+extern IVIDTRANSCODE_Fxns TRIKB200_OL_FXNS;
+extern IVIDTRANSCODE_Fxns TRIKB200_OM_FXNS;
+extern IALG_Fxns TRIKB200_WO_IALG;
+extern IALG_Fxns TRIKB200_WL_IALG;
+extern IALG_Fxns TRIKB200_OO_IALG;
+extern IALG_Fxns TRIKB200_OL_IALG;
+extern IALG_Fxns TRIKB200_OM_IALG;
+
+/* table lookup by kind (NULL if kind is out of range) */
+IVIDTRANSCODE_Fxns* trikb200_fxns(XDAS_Int32 kind);
+
+/* sizes a caller needs without including this header (ctypes / cgo / JNI bindings) */
+XDAS_Int32 trikb200_sizeofInArgsAlg(XDAS_Int32 kind);
+XDAS_Int32 trikb200_sizeofOutArgsAlg(XDAS_Int32 kind);
+XDAS_Int32 trikb200_sizeofInArgs(XDAS_Int32 kind);
+XDAS_Int32 trikb200_sizeofOutArgs(XDAS_Int32 kind);
+XDAS_Int32 trikb200_sizeofHandle(void);
+
+/* ---- surface 2: batch extension --------------------------------------------------------------
+ * Convenience constructor: alloc -> malloc the records -> algInit -> control(XDM_SETPARAMS) for a
+ * width x height input whose preview output is outWidth x outHeight (0,0 = same as input).
+ * lineLength 0 = tight (2*width for YUV422, width for YUV422P).  Limits of the reference's static
+ * buffers (640x480) do not apply: maxWidth/maxHeight default to the requested size.
+ * Returns NULL on failure (same conditions as initObj/control failing). */
+IVIDTRANSCODE_Handle trikb200_create(XDAS_Int32 kind, XDAS_Int32 width, XDAS_Int32 height,
+                                     XDAS_Int32 lineLength, XDAS_Int32 outWidth, XDAS_Int32 outHeight);
+void trikb200_delete(IVIDTRANSCODE_Handle handle);
+
+#define TRIKB200_MEM_HOST   0   /* frames / results are host memory (pageable or pinned) */
+#define TRIKB200_MEM_DEVICE 1   /* frames / results are CUDA device memory on the handle's device */
+
+#define TRIKB200_BATCH_ASYNC 1  /* enqueue only: results land in stream order; needs results in
+                                   device or pinned host memory and no frame that needs the host
+                                   annealing tail (autoDetectHsv on WL/OL/OO), else XDM_EFAIL */
+
+typedef struct TRIKB200_Batch {
+    XDAS_Int32  size;          /* sizeof(TRIKB200_Batch) */
+    XDAS_Int32  numFrames;
+    const void* frames;        /* frame i at frames + i*frameStride */
+    int64_t     frameStride;   /* bytes, multiple of 16 */
+    XDAS_Int32  framesMem;     /* TRIKB200_MEM_* */
+    const void* inArgsAlg;     /* numFrames InArgsAlg of the handle's kind, or ONE when inArgsStride == 0 (host memory) */
+    XDAS_Int32  inArgsStride;  /* bytes between consecutive InArgsAlg, 0 = broadcast the first */
+    void*       outArgsAlg;    /* numFrames OutArgsAlg of the handle's kind */
+    XDAS_Int32  outArgsStride; /* bytes between consecutive OutArgsAlg (>= sizeof) */
+    XDAS_Int32  outArgsMem;    /* TRIKB200_MEM_*; with MEM_DEVICE every field the sensor does not produce is written as 0 */
+    const int64_t* seeds;      /* per-frame srand() seed for the annealed auto-detect, NULL = time(NULL) as the reference */
+    void*       stream;        /* cudaStream_t, NULL = the handle's stream */
+    XDAS_Int32  flags;         /* TRIKB200_BATCH_* */
+} TRIKB200_Batch;
+
+/* n frames through one handle == n sequential process() calls (without the preview image).
+ * Returns IVIDTRANSCODE_EOK, or IVIDTRANSCODE_EFAIL (bad pointers / sizes / CUDA error) with
+ * nothing written to outArgsAlg. */
+XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Batch* batch);
+
+/* wait for everything enqueued on the handle (TRIKB200_BATCH_ASYNC) */
+XDAS_Int32 trikb200_synchronize(IVIDTRANSCODE_Handle handle);
+
+/* seed used by the next process() call that runs an annealed auto-detect (the reference calls
+ * srand(time(NULL)), ov7670/object_sensor/include/internal/cv_hsv_range_detector.hpp:180);
+ * negative = back to time(NULL). */
+void trikb200_setSeed(IVIDTRANSCODE_Handle handle, int64_t seed);
+
+/* device selection for handles created afterwards on this thread (default: current CUDA device) */
+XDAS_Int32 trikb200_deviceCount(void);
+XDAS_Int32 trikb200_setDevice(XDAS_Int32 device);
+
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t trikb200_launchCount(void);
+/* tuning knob: CTAs per frame for the sum kernels (0 = heuristic) */
+void trikb200_setSlabsPerFrame(XDAS_Int32 slabs);
+/* last CUDA / argument error message of this thread ("" if none) */
+const char* trikb200_lastError(void);
+
+/* diagnostics for the parity tests: run the DEVICE pixel functions over a range of inputs.
+ * which = 0: index = Y | U<<8 | V<<16 -> 0x00RRGGBB (bit 31 set if the YUYV and YUV422P lane
+ * paths disagree); which = 1: index = 0x00RRGGBB -> 0x00VVSSHH.  hostOut holds count words. */
+XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count, uint32_t* hostOut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIK_B200_H_ */

@@ -1,0 +1,865 @@
+// trik_capi.cu -- the C ABI of libtrikb200 (include/trik_b200.h): the reference's codec surface
+// (alloc / initObj / free / process / control, <sensor>/src/vidtranscode_cv_fxns.c:85-334 and the
+// handle/dispatch layer <sensor>/src/vidtranscode_cv.cpp:22-320) plus the batch extension.
+//
+// There is NO CPU fallback: every pixel of every frame goes through the CUDA kernels, and any
+// CUDA failure is reported as IVIDTRANSCODE_EFAIL / IALG_EFAIL with trikb200_lastError() set.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <climits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "trik_b200.h"
+#include "trik_host.hpp"
+#include "trik_kernels.cuh"
+
+using namespace trikb200;
+
+namespace {
+
+thread_local std::string t_lastError;
+thread_local int t_device = -1;
+int g_slabsPerFrame = 0;
+
+void set_error(const char* what, cudaError_t e = cudaSuccess)
+{
+  t_lastError = what;
+  if (e != cudaSuccess)
+  {
+    t_lastError += ": ";
+    t_lastError += cudaGetErrorString(e);
+  }
+}
+
+#define CUDA_TRY(expr)                                   \
+  do {                                                   \
+    cudaError_t e__ = (expr);                            \
+    if (e__ != cudaSuccess) { set_error(#expr, e__); return false; } \
+  } while (0)
+
+const size_t kFastRamSize = 0x1000;          // include/internal/vidtranscode_cv.h:28
+const char   kVersion[]   = "1.00.00.00";    // src/vidtranscode_cv_fxns.c:75
+
+// The handle the caller allocates from the alloc() table: IALG_Obj first (vidtranscode_cv.h:17-27).
+struct TrikB200Handle {
+  IALG_Obj                           alg;
+  XDAS_Int32                         kind;
+  TRIK_VIDTRANSCODE_CV_Params        params;
+  TRIK_VIDTRANSCODE_CV_DynamicParams dynamicParams;
+  void*                              impl;       // Instance*
+  XDAS_Int8*                         fastRam;
+  size_t                             fastRamSize;
+};
+
+size_t in_args_alg_size(int kind)
+{
+  switch (kind)
+  {
+    case KIND_OO: return sizeof(TRIKB200_ObjInArgsAlg);
+    case KIND_OM: return sizeof(TRIKB200_MxnInArgsAlg);
+    default:      return sizeof(TRIKB200_RangeInArgsAlg);
+  }
+}
+size_t out_args_alg_size(int kind)
+{
+  switch (kind)
+  {
+    case KIND_OO: return sizeof(TRIKB200_ObjOutArgsAlg);
+    case KIND_OM: return sizeof(TRIKB200_MxnOutArgsAlg);
+    default:      return sizeof(TRIKB200_TargetOutArgsAlg);
+  }
+}
+size_t in_args_size(int kind)
+{
+  switch (kind)
+  {
+    case KIND_OO: return sizeof(TRIKB200_ObjInArgs);
+    case KIND_OM: return sizeof(TRIKB200_MxnInArgs);
+    default:      return sizeof(TRIKB200_RangeInArgs);
+  }
+}
+size_t out_args_size(int kind)
+{
+  switch (kind)
+  {
+    case KIND_OO: return sizeof(TRIKB200_ObjOutArgs);
+    case KIND_OM: return sizeof(TRIKB200_MxnOutArgs);
+    default:      return sizeof(TRIKB200_TargetOutArgs);
+  }
+}
+XDAS_Int32 default_input_format(int kind)
+{
+  return kind_is_planar(kind) ? TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P : TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Instance: the "CVAlgorithm" object of a handle.  Re-created by every SETPARAMS, as the
+// reference re-creates its algorithm object (src/vidtranscode_cv.cpp:52-66).
+// ---------------------------------------------------------------------------------------------
+struct Instance {
+  int          kind = 0;
+  int          device = 0;
+  bool         valid = false;        // setup() accepted the geometry
+  Geometry     geo{};
+  int          outWidth = 0, outHeight = 0, outLineLength = 0;
+  CarriedState state;
+  int64_t      seed = -1;
+  cudaStream_t stream = nullptr;
+
+  // device workspace, grown on demand
+  uint8_t*     dFrames = nullptr;   size_t dFramesCap = 0;
+  FrameParams* dParams = nullptr;   size_t dParamsCap = 0;     // entries
+  SumAcc*      dAcc = nullptr;      size_t dAccCap = 0;        // entries
+  uint8_t*     dOut = nullptr;      size_t dOutCap = 0;        // bytes
+  // pinned host staging
+  FrameParams* hParams = nullptr;   size_t hParamsCap = 0;
+  uint8_t*     hOut = nullptr;      size_t hOutCap = 0;
+
+  ~Instance() { release(); }
+
+  void release()
+  {
+    if (stream || dFrames || dParams || dAcc || dOut || hParams || hOut)
+      cudaSetDevice(device);
+    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); stream = nullptr; }
+    cudaFree(dFrames); dFrames = nullptr; dFramesCap = 0;
+    cudaFree(dParams); dParams = nullptr; dParamsCap = 0;
+    cudaFree(dAcc);    dAcc = nullptr;    dAccCap = 0;
+    cudaFree(dOut);    dOut = nullptr;    dOutCap = 0;
+    cudaFreeHost(hParams); hParams = nullptr; hParamsCap = 0;
+    cudaFreeHost(hOut);    hOut = nullptr;    hOutCap = 0;
+  }
+
+  bool init_device()
+  {
+    int dev = t_device;
+    if (dev < 0)
+      CUDA_TRY(cudaGetDevice(&dev));
+    device = dev;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    return true;
+  }
+
+  size_t frame_bytes() const
+  {
+    return (size_t)geo.height * geo.lineLength * (kind_is_planar(kind) ? 2u : 1u);
+  }
+
+  template <typename T>
+  bool grow_device(T*& p, size_t& cap, size_t want, bool zero)
+  {
+    if (want <= cap)
+      return true;
+    size_t ncap = cap ? cap : 1;
+    while (ncap < want) ncap *= 2;
+    T* np = nullptr;
+    CUDA_TRY(cudaMalloc(&np, ncap * sizeof(T)));
+    if (zero)
+      CUDA_TRY(cudaMemsetAsync(np, 0, ncap * sizeof(T), stream));
+    if (p)
+    {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      cudaFree(p);
+    }
+    p = np; cap = ncap;
+    return true;
+  }
+  template <typename T>
+  bool grow_pinned(T*& p, size_t& cap, size_t want)
+  {
+    if (want <= cap)
+      return true;
+    size_t ncap = cap ? cap : 1;
+    while (ncap < want) ncap *= 2;
+    T* np = nullptr;
+    CUDA_TRY(cudaMallocHost(&np, ncap * sizeof(T)));
+    if (p)
+    {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      cudaFreeHost(p);
+    }
+    p = np; cap = ncap;
+    return true;
+  }
+};
+
+Instance* instance_of(TrikB200Handle* h) { return reinterpret_cast<Instance*>(h->impl); }
+
+// CVAlgorithm::setup(): size rules of webcam/object_sensor/.../cv_ball_detector_seqpass.hpp:365-369
+bool instance_setup(Instance* in, int width, int height, int lineLength, int outW, int outH, int outLine)
+{
+  in->valid = false;
+  in->state = CarriedState();
+  if (width < 0 || height < 0 || width % 32 != 0 || height % 4 != 0)
+    return false;
+  in->geo.width = width;
+  in->geo.height = height;
+  in->geo.lineLength = lineLength;
+  in->geo.frameStride = 0;
+  in->outWidth = outW; in->outHeight = outH; in->outLineLength = outLine;
+  in->valid = true;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the batch core: n frames, host or device, through the kernels
+// ---------------------------------------------------------------------------------------------
+struct BatchView {
+  int            n;
+  const uint8_t* frames; int64_t frameStride; bool framesOnDevice;
+  const uint8_t* inArgs; int inStride;
+  uint8_t*       outArgs; int outStride; bool outOnDevice;
+  const int64_t* seeds;
+  cudaStream_t   stream;
+  bool           async;
+};
+
+// merge a device result record into the caller's OutArgsAlg, touching only the fields the
+// reference's run() assigns for this call
+void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, uint8_t* dst)
+{
+  switch (kind)
+  {
+    case KIND_WO: case KIND_WL: case KIND_OL:
+    {
+      const TargetOut* r = reinterpret_cast<const TargetOut*>(rec);
+      TRIKB200_TargetOutArgsAlg* o = reinterpret_cast<TRIKB200_TargetOutArgsAlg*>(dst);
+      const TRIKB200_RangeInArgsAlg* ia = reinterpret_cast<const TRIKB200_RangeInArgsAlg*>(inArgsAlg);
+      o->targetX = r->targetX; o->targetY = r->targetY; o->targetSize = r->targetSize;
+      if (ia->autoDetectHsv)
+      {
+        o->detectHue = r->detectHue; o->detectHueTolerance = r->detectHueTolerance;
+        o->detectSat = r->detectSat; o->detectSatTolerance = r->detectSatTolerance;
+        o->detectVal = r->detectVal; o->detectValTolerance = r->detectValTolerance;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+bool run_batch(Instance* in, const BatchView& b)
+{
+  if (!in->valid || in->geo.width <= 0 || in->geo.height <= 0)
+  {
+    set_error("algorithm not set up for a non-empty image");
+    return false;
+  }
+  const int kind = in->kind;
+  if (kind != KIND_WO && kind != KIND_WL && kind != KIND_OL)
+  {
+    set_error("sensor kind not available in this build");
+    return false;
+  }
+  CUDA_TRY(cudaSetDevice(in->device));
+  cudaStream_t s = b.stream ? b.stream : in->stream;
+  const size_t fbytes = in->frame_bytes();
+  const size_t recBytes = sizeof(TargetOut);
+
+  // 1. per-frame parameters (carried state advances frame by frame, as n process() calls would)
+  const bool broadcast = (b.inStride == 0) && kind != KIND_OL && kind != KIND_OO;
+  const size_t np = broadcast ? 1 : (size_t)b.n;
+  if (!in->grow_pinned(in->hParams, in->hParamsCap, np)) return false;
+  if (!in->grow_device(in->dParams, in->dParamsCap, np, false)) return false;
+  for (size_t i = 0; i < np; ++i)
+    prepare_frame_params(kind, in->geo, b.inArgs + i * (size_t)b.inStride, in->state, in->hParams[i]);
+  CUDA_TRY(cudaMemcpyAsync(in->dParams, in->hParams, np * sizeof(FrameParams), cudaMemcpyHostToDevice, s));
+
+  // 2. frames
+  Geometry g = in->geo;
+  const uint8_t* dFrames = b.frames;
+  if (b.framesOnDevice)
+    g.frameStride = b.frameStride;
+  else
+  {
+    const size_t stride = (fbytes + 15u) & ~(size_t)15u;
+    if (!in->grow_device(in->dFrames, in->dFramesCap, stride * b.n, false)) return false;
+    if (b.frameStride == (int64_t)stride || b.n == 1)
+      CUDA_TRY(cudaMemcpyAsync(in->dFrames, b.frames, b.n == 1 ? fbytes : stride * b.n, cudaMemcpyHostToDevice, s));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(in->dFrames, stride, b.frames, (size_t)b.frameStride, fbytes, b.n, cudaMemcpyHostToDevice, s));
+    dFrames = in->dFrames;
+    g.frameStride = (int64_t)stride;
+  }
+
+  // 3. kernels
+  if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
+  uint8_t* dOut;
+  if (b.outOnDevice && b.outStride == (int)recBytes)
+    dOut = b.outArgs;
+  else
+  {
+    if (!in->grow_device(in->dOut, in->dOutCap, recBytes * b.n, false)) return false;
+    dOut = in->dOut;
+  }
+  CUDA_TRY(launch_sum_sensor(kind, g, b.n, dFrames, in->dParams, broadcast ? 0 : 1, in->dAcc,
+                             reinterpret_cast<TargetOut*>(dOut), g_slabsPerFrame, s));
+
+  // 4. results
+  if (b.outOnDevice)
+  {
+    if (dOut != b.outArgs)
+      CUDA_TRY(cudaMemcpy2DAsync(b.outArgs, (size_t)b.outStride, dOut, recBytes, recBytes, b.n, cudaMemcpyDeviceToDevice, s));
+    if (!b.async)
+      CUDA_TRY(cudaStreamSynchronize(s));
+    return true;
+  }
+  if (b.async)
+  {
+    // pinned host results, whole records (documented: fields the sensor does not produce are 0)
+    CUDA_TRY(cudaMemcpy2DAsync(b.outArgs, (size_t)b.outStride, dOut, recBytes, recBytes, b.n, cudaMemcpyDeviceToHost, s));
+    return true;
+  }
+  if (!in->grow_pinned(in->hOut, in->hOutCap, recBytes * b.n)) return false;
+  CUDA_TRY(cudaMemcpyAsync(in->hOut, dOut, recBytes * b.n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < b.n; ++i)
+    merge_result(kind, b.inArgs + (size_t)i * b.inStride, in->hOut + (size_t)i * recBytes, b.outArgs + (size_t)i * b.outStride);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle / dispatch layer: src/vidtranscode_cv.cpp
+// ---------------------------------------------------------------------------------------------
+XDAS_Int32 handle_setup_image_desc(TrikB200Handle* h)     // vidtranscode_cv.cpp:90-145
+{
+  Instance* in = instance_of(h);
+  const IVIDTRANSCODE_Params& pb = h->params.base;
+  const TRIK_VIDTRANSCODE_CV_DynamicParams& dp = h->dynamicParams;
+  if (pb.numOutputStreams != 0 && pb.numOutputStreams != 1)
+    return IALG_EFAIL;
+
+  // TrikCvImageDimension is XDAS_Int16 (include/internal/vidtranscode_cv.h:32)
+  const XDAS_Int16 inW = (XDAS_Int16)(dp.inputWidth  > 0 ? dp.inputWidth  : 0);
+  const XDAS_Int16 inH = (XDAS_Int16)(dp.inputHeight > 0 ? dp.inputHeight : 0);
+  const XDAS_Int32 inLine = dp.inputLineLength > 0 ? dp.inputLineLength : 0;
+  XDAS_Int16 outW = 0, outH = 0;
+  XDAS_Int32 outLine = 0, outFormat = TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_UNKNOWN;
+  if (pb.numOutputStreams == 1)
+  {
+    outFormat = pb.formatOutput[0];
+    outW = (XDAS_Int16)(dp.base.outputWidth[0]  > 0 ? dp.base.outputWidth[0]  : 0);
+    outH = (XDAS_Int16)(dp.base.outputHeight[0] > 0 ? dp.base.outputHeight[0] : 0);
+    outLine = dp.outputLineLength[0] > 0 ? dp.outputLineLength[0] : 0;
+  }
+  if (   (inW  < 0 || inW  > pb.maxWidthInput)
+      || (inH  < 0 || inH  > pb.maxHeightInput)
+      || (outW < 0 || outW > pb.maxWidthOutput[0])
+      || (outH < 0 || outH > pb.maxHeightOutput[0]))
+    return IALG_EFAIL;
+
+  // only the sensor's own (input format, RGB565X) pair exists (vidtranscode_cv.cpp:76-84)
+  if (pb.formatInput != default_input_format(h->kind) || outFormat != TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_RGB565X)
+    return IALG_EFAIL;
+
+  if (!instance_setup(in, inW, inH, inLine, outW, outH, outLine))
+    return IALG_EFAIL;
+  return IALG_EOK;
+}
+
+XDAS_Int32 handle_setup_params(TrikB200Handle* h, const TRIK_VIDTRANSCODE_CV_Params* params)   // :150-197
+{
+  TRIK_VIDTRANSCODE_CV_Params def;
+  memset(&def, 0, sizeof(def));
+  def.base.size = sizeof(TRIK_VIDTRANSCODE_CV_Params);
+  def.base.numOutputStreams = 1;
+  def.base.formatInput = default_input_format(h->kind);
+  def.base.formatOutput[0] = TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_RGB565X;
+  def.base.formatOutput[1] = TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_UNKNOWN;
+  def.base.maxHeightInput = 480;
+  def.base.maxWidthInput = 640;
+  def.base.maxFrameRateInput = 60000;
+  def.base.maxBitRateInput = -1;
+  def.base.maxHeightOutput[0] = 480; def.base.maxHeightOutput[1] = -1;
+  def.base.maxWidthOutput[0] = 640;  def.base.maxWidthOutput[1] = -1;
+  def.base.maxFrameRateOutput[0] = def.base.maxFrameRateOutput[1] = -1;
+  def.base.maxBitRateOutput[0] = def.base.maxBitRateOutput[1] = -1;
+  def.base.dataEndianness = XDM_BYTE;
+  h->params = params ? *params : def;
+  return IALG_EOK;
+}
+
+XDAS_Int32 handle_setup_dynamic_params(TrikB200Handle* h, const TRIK_VIDTRANSCODE_CV_DynamicParams* dyn)  // :202-286
+{
+  TRIK_VIDTRANSCODE_CV_DynamicParams def;
+  memset(&def, 0, sizeof(def));
+  def.base.size = sizeof(TRIK_VIDTRANSCODE_CV_DynamicParams);
+  def.base.readHeaderOnlyFlag = 0;
+  def.base.keepInputResolutionFlag[0] = XDAS_FALSE; def.base.keepInputResolutionFlag[1] = XDAS_TRUE;
+  // line sensors default to a 240 wide x 320 high preview (line_sensor/src/vidtranscode_cv.cpp:214,218)
+  const bool line = (h->kind == KIND_WL || h->kind == KIND_OL);
+  def.base.outputHeight[0] = line ? 320 : 240; def.base.outputHeight[1] = 0;
+  def.base.outputWidth[0]  = line ? 240 : 320; def.base.outputWidth[1] = 0;
+  def.base.keepInputFrameRateFlag[0] = def.base.keepInputFrameRateFlag[1] = XDAS_TRUE;
+  def.base.inputFrameRate = -1;
+  def.base.outputFrameRate[0] = def.base.outputFrameRate[1] = -1;
+  def.base.targetBitRate[0] = def.base.targetBitRate[1] = -1;
+  def.base.rateControl[0] = def.base.rateControl[1] = IVIDEO_NONE;
+  def.base.keepInputGOPFlag[0] = def.base.keepInputGOPFlag[1] = XDAS_TRUE;
+  def.base.intraFrameInterval[0] = def.base.intraFrameInterval[1] = 1;
+  def.base.interFrameInterval[0] = def.base.interFrameInterval[1] = 0;
+  def.base.forceFrame[0] = def.base.forceFrame[1] = IVIDEO_NA_FRAME;
+  def.base.frameSkipTranscodeFlag[0] = def.base.frameSkipTranscodeFlag[1] = XDAS_FALSE;
+  def.inputHeight = -1; def.inputWidth = -1; def.inputLineLength = -1;
+  def.outputLineLength[0] = def.outputLineLength[1] = -1;
+  h->dynamicParams = dyn ? *dyn : def;
+  return handle_setup_image_desc(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// IALG + IVIDTRANSCODE entry points, shared by the five kinds
+// ---------------------------------------------------------------------------------------------
+Int alg_alloc(const IALG_Params*, IALG_Fxns**, IALG_MemRec memTab[])          // fxns.c:85-102
+{
+  memTab[0].size = sizeof(TrikB200Handle);
+  memTab[0].alignment = 0;
+  memTab[0].space = IALG_EXTERNAL;
+  memTab[0].attrs = IALG_PERSIST;
+  memTab[1].size = kFastRamSize;
+  memTab[1].alignment = 0;
+  memTab[1].space = IALG_DARAM0;
+  memTab[1].attrs = IALG_PERSIST;
+  return 2;
+}
+
+Int alg_free(IALG_Handle algHandle, IALG_MemRec memTab[])                      // fxns.c:114-136
+{
+  TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(algHandle);
+  delete instance_of(h);                                                      // trikCvHandleDestroy
+  h->impl = nullptr;
+  memTab[0].base = h;
+  memTab[0].size = sizeof(TrikB200Handle);
+  memTab[0].alignment = 0;
+  memTab[0].space = IALG_EXTERNAL;
+  memTab[0].attrs = IALG_PERSIST;
+  memTab[1].base = h->fastRam;
+  memTab[1].size = (Uns)h->fastRamSize;
+  memTab[1].alignment = 0;
+  memTab[1].space = IALG_DARAM0;
+  memTab[1].attrs = IALG_PERSIST;
+  return 2;
+}
+
+Int alg_init(int kind, IALG_Handle algHandle, const IALG_MemRec memTab[], const IALG_Params* algParams)  // fxns.c:146-166
+{
+  TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(algHandle);
+  h->kind = kind;
+  h->fastRam = reinterpret_cast<XDAS_Int8*>(memTab[1].base);
+  h->fastRamSize = memTab[1].size;
+  Instance* in = new (std::nothrow) Instance();                               // trikCvHandleInit
+  if (!in)
+    return IALG_EFAIL;
+  in->kind = kind;
+  h->impl = in;
+  if (!in->init_device())
+    return IALG_EFAIL;
+  XDAS_Int32 res;
+  if ((res = handle_setup_params(h, reinterpret_cast<const TRIK_VIDTRANSCODE_CV_Params*>(algParams))) != IALG_EOK)
+    return res;
+  if ((res = handle_setup_dynamic_params(h, nullptr)) != IALG_EOK)
+    return res;
+  return IALG_EOK;
+}
+
+XDAS_Int32 vid_process(int kind, IVIDTRANSCODE_Handle algHandle, XDM1_BufDesc* inBufs, XDM_BufDesc* outBufs,
+                       IVIDTRANSCODE_InArgs* vidInArgs, IVIDTRANSCODE_OutArgs* vidOutArgs)   // fxns.c:174-264
+{
+  TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(algHandle);
+  if (   vidInArgs->size  != (XDAS_Int32)in_args_size(kind)
+      || vidOutArgs->size != (XDAS_Int32)out_args_size(kind))
+  {
+    XDM_SETUNSUPPORTEDPARAM(vidOutArgs->extendedError);
+    return IVIDTRANSCODE_EUNSUPPORTED;
+  }
+  if (inBufs->numBufs != 1 || outBufs->numBufs < h->params.base.numOutputStreams)
+  {
+    XDM_SETUNSUPPORTEDPARAM(vidOutArgs->extendedError);
+    return IVIDTRANSCODE_EFAIL;
+  }
+  XDM1_SingleBufDesc* inBuf = &inBufs->descs[0];
+  if (inBuf->buf == NULL || vidInArgs->numBytes < 0 || vidInArgs->numBytes > inBuf->bufSize)
+  {
+    XDM_SETUNSUPPORTEDPARAM(vidOutArgs->extendedError);
+    return IVIDTRANSCODE_EFAIL;
+  }
+
+  XDM_SETACCESSMODE_READ(inBuf->accessMask);
+  vidOutArgs->bitsConsumed            = vidInArgs->numBytes * CHAR_BIT;
+  vidOutArgs->decodedPictureType      = IVIDEO_NA_PICTURE;
+  vidOutArgs->decodedPictureStructure = IVIDEO_CONTENTTYPE_NA;
+  vidOutArgs->decodedHeight           = h->dynamicParams.inputHeight;
+  vidOutArgs->decodedWidth            = h->dynamicParams.inputWidth;
+
+  XDM1_SingleBufDesc* outBuf = NULL;
+  XDAS_Int8* outPtr = NULL;
+  XDAS_Int32 outSize = 0;
+  if (h->params.base.numOutputStreams == 1)
+  {
+    outBuf = &vidOutArgs->encodedBuf[0];
+    outBuf->buf = outBufs->bufs[0];
+    outBuf->bufSize = outBufs->bufSizes[0];
+    outBuf->accessMask = 0;
+    outPtr = outBuf->buf;
+    outSize = outBuf->bufSize;
+    memset(outPtr, 0, (size_t)outSize);                                        // fxns.c:234
+  }
+
+  // trikCvProceedImage + CVAlgorithm::run() entry checks (cv_ball_detector_seqpass.hpp:415-419)
+  Instance* in = instance_of(h);
+  uint8_t* inAlg  = reinterpret_cast<uint8_t*>(vidInArgs)  + sizeof(IVIDTRANSCODE_InArgs);
+  uint8_t* outAlg = reinterpret_cast<uint8_t*>(vidOutArgs) + sizeof(IVIDTRANSCODE_OutArgs);
+  bool ok = (in != nullptr) && in->valid;
+  if (ok)
+  {
+    // YUV422P reads two planes of height*lineLength bytes; the reference only checks one
+    // (ov7670/object_sensor/.../cv_ball_detector_seqpass.hpp:519) and reads past numBytes.  Here the whole
+    // frame must be inside numBytes (documented deviation, DESIGN.md "Boundary").
+    if ((long long)in->frame_bytes() > (long long)vidInArgs->numBytes)
+      ok = false;
+    if ((long long)in->outHeight * in->outLineLength > (long long)outSize)
+      ok = false;
+  }
+  if (ok)
+  {
+    outSize = in->outHeight * in->outLineLength;
+    if (in->geo.width > 0 && in->geo.height > 0)
+    {
+      BatchView b{};
+      b.n = 1;
+      b.frames = reinterpret_cast<const uint8_t*>(inBuf->buf); b.frameStride = 0; b.framesOnDevice = false;
+      b.inArgs = inAlg; b.inStride = (int)in_args_alg_size(kind);
+      b.outArgs = outAlg; b.outStride = (int)out_args_alg_size(kind); b.outOnDevice = false;
+      int64_t seed = in->seed >= 0 ? in->seed : (int64_t)time(NULL);
+      b.seeds = &seed;
+      b.stream = nullptr; b.async = false;
+      ok = run_batch(in, b);
+    }
+    else
+      ok = false; /* the reference would run its tail on a 0x0 image; nothing sensible to produce */
+  }
+  if (!ok)
+  {
+    XDM_SETCORRUPTEDDATA(vidOutArgs->extendedError);
+    return IVIDTRANSCODE_EFAIL;
+  }
+
+  if (outBuf)
+  {
+    outBuf->bufSize = outSize;
+    XDM_SETACCESSMODE_WRITE(outBuf->accessMask);
+    vidOutArgs->bitsGenerated[0]               = outBuf->bufSize * CHAR_BIT;
+    vidOutArgs->encodedPictureType[0]          = vidOutArgs->decodedPictureType;
+    vidOutArgs->encodedPictureStructure[0]     = vidOutArgs->decodedPictureStructure;
+    vidOutArgs->outputID[0]                    = vidInArgs->inputID;
+    vidOutArgs->inputFrameSkipTranscodeFlag[0] = XDAS_FALSE;
+  }
+  vidOutArgs->outBufsInUseFlag = XDAS_FALSE;
+  return IVIDTRANSCODE_EOK;
+}
+
+XDAS_Int32 vid_control(int, IVIDTRANSCODE_Handle algHandle, IVIDTRANSCODE_Cmd cmd,
+                       IVIDTRANSCODE_DynamicParams* dynParams, IVIDTRANSCODE_Status* status)   // fxns.c:272-334
+{
+  TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(algHandle);
+  XDAS_Int32 ret = IVIDTRANSCODE_EFAIL;
+  XDM_CLEARACCESSMODE_READ(status->data.accessMask);
+  XDM_CLEARACCESSMODE_WRITE(status->data.accessMask);
+  switch (cmd)
+  {
+    case XDM_GETSTATUS:
+    case XDM_GETBUFINFO:
+      status->extendedError = 0;
+      status->bufInfo.minNumInBufs = 1;
+      status->bufInfo.minNumOutBufs = 1;
+      status->bufInfo.minInBufSize[0] = 0;
+      status->bufInfo.minOutBufSize[0] = 0;
+      XDM_SETACCESSMODE_WRITE(status->data.accessMask);
+      ret = IVIDTRANSCODE_EOK;
+      break;
+    case XDM_SETPARAMS:
+      if (dynParams->size == (XDAS_Int32)sizeof(TRIK_VIDTRANSCODE_CV_DynamicParams))
+        ret = handle_setup_dynamic_params(h, reinterpret_cast<TRIK_VIDTRANSCODE_CV_DynamicParams*>(dynParams));
+      else
+        ret = IVIDTRANSCODE_EUNSUPPORTED;
+      break;
+    case XDM_RESET:
+    case XDM_SETDEFAULT:
+      ret = handle_setup_dynamic_params(h, nullptr);
+      break;
+    case XDM_FLUSH:
+      ret = IVIDTRANSCODE_EOK;
+      break;
+    case XDM_GETVERSION:
+      if (status->data.buf != NULL && status->data.bufSize >= (XDAS_Int32)(strlen(kVersion) + 1))
+      {
+        memcpy(status->data.buf, kVersion, strlen(kVersion) + 1);
+        XDM_SETACCESSMODE_WRITE(status->data.accessMask);
+        ret = IVIDTRANSCODE_EOK;
+      }
+      else
+        ret = IVIDTRANSCODE_EFAIL;
+      break;
+    default:
+      ret = IVIDTRANSCODE_EFAIL;
+      break;
+  }
+  return ret;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// exported tables, one per sensor kind
+// ---------------------------------------------------------------------------------------------
+#define TRIKB200_DEFINE_KIND(NAME, KIND)                                                                        \
+  static Int NAME##_init(IALG_Handle hh, const IALG_MemRec mt[], IALG_Handle, const IALG_Params* p)             \
+  { return alg_init(KIND, hh, mt, p); }                                                                         \
+  static XDAS_Int32 NAME##_process(IVIDTRANSCODE_Handle hh, XDM1_BufDesc* ib, XDM_BufDesc* ob,                  \
+                                   IVIDTRANSCODE_InArgs* ia, IVIDTRANSCODE_OutArgs* oa)                         \
+  { return vid_process(KIND, hh, ib, ob, ia, oa); }                                                             \
+  static XDAS_Int32 NAME##_control(IVIDTRANSCODE_Handle hh, IVIDTRANSCODE_Cmd c,                                \
+                                   IVIDTRANSCODE_DynamicParams* dp, IVIDTRANSCODE_Status* st)                   \
+  { return vid_control(KIND, hh, c, dp, st); }                                                                  \
+  extern "C" { IALG_Fxns TRIKB200_##NAME##_IALG = {                                                             \
+    &TRIKB200_##NAME##_IALG, NULL, alg_alloc, NULL, NULL, alg_free, NAME##_init, NULL, NULL };                  \
+  IVIDTRANSCODE_Fxns TRIKB200_##NAME##_FXNS = {                                                                 \
+    { &TRIKB200_##NAME##_IALG, NULL, alg_alloc, NULL, NULL, alg_free, NAME##_init, NULL, NULL },                \
+    NAME##_process, NAME##_control }; }
+
+extern "C" {
+extern IALG_Fxns TRIKB200_WO_IALG, TRIKB200_WL_IALG, TRIKB200_OO_IALG, TRIKB200_OL_IALG, TRIKB200_OM_IALG;
+}
+TRIKB200_DEFINE_KIND(WO, KIND_WO)
+TRIKB200_DEFINE_KIND(WL, KIND_WL)
+TRIKB200_DEFINE_KIND(OO, KIND_OO)
+TRIKB200_DEFINE_KIND(OL, KIND_OL)
+TRIKB200_DEFINE_KIND(OM, KIND_OM)
+
+extern "C" {
+
+IVIDTRANSCODE_Fxns* trikb200_fxns(XDAS_Int32 kind)
+{
+  switch (kind)
+  {
+    case KIND_WO: return &TRIKB200_WO_FXNS;
+    case KIND_WL: return &TRIKB200_WL_FXNS;
+    case KIND_OO: return &TRIKB200_OO_FXNS;
+    case KIND_OL: return &TRIKB200_OL_FXNS;
+    case KIND_OM: return &TRIKB200_OM_FXNS;
+    default: return NULL;
+  }
+}
+
+XDAS_Int32 trikb200_sizeofInArgsAlg(XDAS_Int32 kind)  { return (XDAS_Int32)in_args_alg_size(kind); }
+XDAS_Int32 trikb200_sizeofOutArgsAlg(XDAS_Int32 kind) { return (XDAS_Int32)out_args_alg_size(kind); }
+XDAS_Int32 trikb200_sizeofInArgs(XDAS_Int32 kind)     { return (XDAS_Int32)in_args_size(kind); }
+XDAS_Int32 trikb200_sizeofOutArgs(XDAS_Int32 kind)    { return (XDAS_Int32)out_args_size(kind); }
+XDAS_Int32 trikb200_sizeofHandle(void)                { return (XDAS_Int32)sizeof(TrikB200Handle); }
+
+IVIDTRANSCODE_Handle trikb200_create(XDAS_Int32 kind, XDAS_Int32 width, XDAS_Int32 height,
+                                     XDAS_Int32 lineLength, XDAS_Int32 outWidth, XDAS_Int32 outHeight)
+{
+  IVIDTRANSCODE_Fxns* fx = trikb200_fxns(kind);
+  if (!fx)
+  {
+    set_error("unknown sensor kind");
+    return NULL;
+  }
+  if (outWidth <= 0) outWidth = width;
+  if (outHeight <= 0) outHeight = height;
+  if (lineLength <= 0) lineLength = kind_is_planar(kind) ? width : 2 * width;
+
+  TRIK_VIDTRANSCODE_CV_Params params;
+  memset(&params, 0, sizeof(params));
+  params.base.size = sizeof(params);
+  params.base.numOutputStreams = 1;
+  params.base.formatInput = default_input_format(kind);
+  params.base.formatOutput[0] = TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_RGB565X;
+  params.base.maxHeightInput = height > 480 ? height : 480;
+  params.base.maxWidthInput = width > 640 ? width : 640;
+  params.base.maxFrameRateInput = 60000;
+  params.base.maxBitRateInput = -1;
+  int outMax = outWidth > outHeight ? outWidth : outHeight;
+  if (outMax < 640) outMax = 640;
+  params.base.maxHeightOutput[0] = outMax; params.base.maxHeightOutput[1] = -1;
+  params.base.maxWidthOutput[0] = outMax;  params.base.maxWidthOutput[1] = -1;
+  params.base.maxFrameRateOutput[0] = params.base.maxFrameRateOutput[1] = -1;
+  params.base.maxBitRateOutput[0] = params.base.maxBitRateOutput[1] = -1;
+  params.base.dataEndianness = XDM_BYTE;
+
+  IALG_MemRec memTab[IALG_DEFMEMRECS];
+  memset(memTab, 0, sizeof(memTab));
+  IALG_Fxns* parent = NULL;
+  const int n = fx->ialg.algAlloc(reinterpret_cast<const IALG_Params*>(&params), &parent, memTab);
+  for (int i = 0; i < n; ++i)
+  {
+    memTab[i].base = calloc(1, memTab[i].size ? memTab[i].size : 1);
+    if (!memTab[i].base)
+      return NULL;
+  }
+  IALG_Handle alg = reinterpret_cast<IALG_Handle>(memTab[0].base);
+  alg->fxns = &fx->ialg;
+  bool ok = fx->ialg.algInit(alg, memTab, NULL, reinterpret_cast<const IALG_Params*>(&params)) == IALG_EOK;
+  if (ok)
+  {
+    TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(alg);
+    TRIK_VIDTRANSCODE_CV_DynamicParams dyn = h->dynamicParams;   // the defaults initObj installed
+    dyn.base.outputHeight[0] = outHeight;
+    dyn.base.outputWidth[0] = outWidth;
+    dyn.inputHeight = height;
+    dyn.inputWidth = width;
+    dyn.inputLineLength = lineLength;
+    dyn.outputLineLength[0] = outWidth * 2;
+    IVIDTRANSCODE_Status status;
+    memset(&status, 0, sizeof(status));
+    status.size = sizeof(status);
+    ok = fx->control(reinterpret_cast<IVIDTRANSCODE_Handle>(alg), XDM_SETPARAMS,
+                     reinterpret_cast<IVIDTRANSCODE_DynamicParams*>(&dyn), &status) == IVIDTRANSCODE_EOK;
+    if (!ok)
+      set_error("control(XDM_SETPARAMS) rejected the geometry");
+  }
+  if (!ok)
+  {
+    trikb200_delete(reinterpret_cast<IVIDTRANSCODE_Handle>(alg));
+    return NULL;
+  }
+  return reinterpret_cast<IVIDTRANSCODE_Handle>(alg);
+}
+
+void trikb200_delete(IVIDTRANSCODE_Handle handle)
+{
+  if (!handle)
+    return;
+  IALG_MemRec memTab[IALG_DEFMEMRECS];
+  memset(memTab, 0, sizeof(memTab));
+  const int n = alg_free(reinterpret_cast<IALG_Handle>(handle), memTab);
+  for (int i = n - 1; i >= 0; --i)
+    free(memTab[i].base);
+}
+
+XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Batch* batch)
+{
+  TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(handle);
+  if (!h || !batch || batch->size != (XDAS_Int32)sizeof(TRIKB200_Batch))
+  {
+    set_error("bad handle or TRIKB200_Batch.size");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  Instance* in = instance_of(h);
+  if (!in || batch->numFrames < 0 || (batch->numFrames > 0 && (!batch->frames || !batch->inArgsAlg || !batch->outArgsAlg)))
+  {
+    set_error("null batch pointers");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if (batch->numFrames == 0)
+    return IVIDTRANSCODE_EOK;
+  const size_t fbytes = in->frame_bytes();
+  if (batch->numFrames > 1 && ((size_t)batch->frameStride < fbytes || (batch->frameStride & 15)))
+  {
+    set_error("frameStride must cover a frame and be a multiple of 16");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if (batch->framesMem == TRIKB200_MEM_DEVICE && (((uintptr_t)batch->frames & 15) || (in->geo.lineLength & 15)))
+  {
+    set_error("device frames must be 16-byte aligned with a 16-byte multiple lineLength");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if ((in->geo.lineLength & 15) != 0)
+  {
+    set_error("inputLineLength must be a multiple of 16");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if (batch->outArgsStride < (XDAS_Int32)out_args_alg_size(h->kind)
+      || (batch->inArgsStride != 0 && batch->inArgsStride < (XDAS_Int32)in_args_alg_size(h->kind)))
+  {
+    set_error("inArgsStride / outArgsStride smaller than the sensor's structs");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  BatchView b{};
+  b.n = batch->numFrames;
+  b.frames = reinterpret_cast<const uint8_t*>(batch->frames);
+  b.frameStride = batch->frameStride;
+  b.framesOnDevice = (batch->framesMem == TRIKB200_MEM_DEVICE);
+  b.inArgs = reinterpret_cast<const uint8_t*>(batch->inArgsAlg);
+  b.inStride = batch->inArgsStride;
+  b.outArgs = reinterpret_cast<uint8_t*>(batch->outArgsAlg);
+  b.outStride = batch->outArgsStride;
+  b.outOnDevice = (batch->outArgsMem == TRIKB200_MEM_DEVICE);
+  b.seeds = batch->seeds;
+  b.stream = reinterpret_cast<cudaStream_t>(batch->stream);
+  b.async = (batch->flags & TRIKB200_BATCH_ASYNC) != 0;
+  return run_batch(in, b) ? IVIDTRANSCODE_EOK : IVIDTRANSCODE_EFAIL;
+}
+
+XDAS_Int32 trikb200_synchronize(IVIDTRANSCODE_Handle handle)
+{
+  TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(handle);
+  Instance* in = h ? instance_of(h) : nullptr;
+  if (!in)
+    return IVIDTRANSCODE_EFAIL;
+  cudaSetDevice(in->device);
+  cudaError_t e = cudaStreamSynchronize(in->stream);
+  if (e != cudaSuccess)
+  {
+    set_error("cudaStreamSynchronize", e);
+    return IVIDTRANSCODE_EFAIL;
+  }
+  return IVIDTRANSCODE_EOK;
+}
+
+void trikb200_setSeed(IVIDTRANSCODE_Handle handle, int64_t seed)
+{
+  TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(handle);
+  if (h && instance_of(h))
+    instance_of(h)->seed = seed;
+}
+
+XDAS_Int32 trikb200_deviceCount(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+XDAS_Int32 trikb200_setDevice(XDAS_Int32 device)
+{
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess)
+  {
+    set_error("cudaSetDevice", e);
+    return IVIDTRANSCODE_EFAIL;
+  }
+  t_device = device;
+  return IVIDTRANSCODE_EOK;
+}
+
+int64_t trikb200_launchCount(void) { return launch_count(); }
+void trikb200_setSlabsPerFrame(XDAS_Int32 slabs) { g_slabsPerFrame = slabs; }
+const char* trikb200_lastError(void) { return t_lastError.c_str(); }
+
+/* test probes: exhaustive pixel functions straight from the device code (tests/test_pixel_gpu.py) */
+XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count, uint32_t* hostOut)
+{
+  uint32_t* d = nullptr;
+  if (cudaMalloc(&d, (size_t)count * 4) != cudaSuccess)
+    return IVIDTRANSCODE_EFAIL;
+  cudaError_t e = which == 0 ? launch_probe_yuv2rgb(first, count, d, 0) : launch_probe_rgb2hsv(first, count, d, 0);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(hostOut, d, (size_t)count * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess)
+  {
+    set_error("probe", e);
+    return IVIDTRANSCODE_EFAIL;
+  }
+  return IVIDTRANSCODE_EOK;
+}
+
+} // extern "C"

@@ -1,0 +1,68 @@
+// trik_kernels.cuh -- device-side data layout and launcher declarations (internal to libtrikb200).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace trikb200 {
+
+enum Kind : int { KIND_WO = 0, KIND_WL = 1, KIND_OO = 2, KIND_OL = 3, KIND_OM = 4, KIND_COUNT = 5 };
+
+__host__ __device__ inline bool kind_is_planar(int kind) { return kind == KIND_OO || kind == KIND_OL || kind == KIND_OM; }
+
+// Geometry of one sensor instance (what CVAlgorithm::setup() receives).
+struct Geometry {
+  int32_t width, height;      // pixels; width % 32 == 0, height % 4 == 0
+  int32_t lineLength;         // byte stride of a row (of each plane for YUV422P)
+  int64_t frameStride;        // bytes between frames of a batch
+};
+
+// Per-frame parameters, prepared on the host from InArgsAlg + the handle's carried state.
+struct FrameParams {
+  // line sensors (V-only threshold in the key domain, see trik_pixel.cuh)
+  uint32_t negKlo2;           // both lanes: (-klo) mod 2^16
+  uint32_t n2;                // both lanes: N = khi - klo;  pass <=> ((key - klo) mod 2^16) <= N
+  uint32_t hStart, hStop;     // OL cross band of THIS frame (lags one frame, OL/.../cv_line_detector_seqpass.hpp:449-450)
+  // full HSV threshold (WO, OO): packed 0x00VVSSHH bounds and expected compare mask
+  uint32_t from, to, expected;
+  // OM grid
+  uint32_t gridRows, gridCols; // m_heightM (= inArgs.widthM), m_widthN (= inArgs.heightN)
+  uint32_t flags;             // FP_* bits
+  uint32_t pad[2];
+};
+constexpr uint32_t FP_AUTODETECT = 1u;
+
+// Raw per-frame accumulators of the sum kernels; zero before the first launch and reset to zero
+// by the CTA that finalises the frame, so back-to-back launches need no memset.
+struct SumAcc {
+  uint32_t fails;             // pixels inside the counting window that FAIL the threshold
+  uint32_t sxFail;            // sum of their columns
+  uint32_t syFail;            // sum of their rows (WO)
+  uint32_t crossFail;         // fails inside rows hStart..hStop (OL)
+  uint32_t done;              // CTAs of this frame that have contributed
+  uint32_t pad[3];
+};
+
+// Device result record of WO / WL / OL == TRIKB200_TargetOutArgsAlg (16 bytes).
+struct TargetOut {
+  int8_t  targetX, targetY;
+  uint8_t targetSize, pad;
+  uint16_t detectHue, detectHueTolerance, detectSat, detectSatTolerance, detectVal, detectValTolerance;
+};
+static_assert(sizeof(TargetOut) == 16, "TargetOutArgsAlg layout");
+
+struct LaunchStats { long long launches; };
+
+// ---- launchers (trik_kernels.cu) ---------------------------------------------------------------
+// params: numFrames entries, or one entry when paramStride == 0.
+cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const uint8_t* frames,
+                              const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,
+                              int slabsPerFrame, cudaStream_t stream);
+
+// exhaustive pixel-function probes for the parity tests: out[i] for i = blockIdx*blockDim+threadIdx
+cudaError_t launch_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
+cudaError_t launch_probe_rgb2hsv(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
+
+int sum_sensor_block_threads(int kind, int width);
+long long launch_count();
+
+} // namespace trikb200
