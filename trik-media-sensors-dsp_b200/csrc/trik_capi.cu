@@ -10,7 +10,9 @@
 #include <ctime>
 #include <climits>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "trik_b200.h"
@@ -115,23 +117,39 @@ struct Instance {
   FrameParams* dParams = nullptr;   size_t dParamsCap = 0;     // entries
   SumAcc*      dAcc = nullptr;      size_t dAccCap = 0;        // entries
   uint8_t*     dOut = nullptr;      size_t dOutCap = 0;        // bytes
+  uint32_t*    dMxnTable = nullptr;                            // 512 colours of the mxn sensor
+  uint16_t*    dBitmaps = nullptr;  size_t dBitmapsCap = 0;    // OO metapixel bitmaps (uint16 entries)
+  uint8_t*     dClusters = nullptr; size_t dClustersCap = 0;   // OO cluster records (bytes)
+  uint16_t*    dEqual = nullptr;    size_t dEqualCap = 0;      // OO label equivalences
+  int*         dFlagged = nullptr;  size_t dFlaggedCap = 0;    // indices of frames that auto-calibrate
+  int32_t*     dHist = nullptr;     size_t dHistCap = 0;       // ordered +1/-2 histograms (int32 entries)
   // pinned host staging
   FrameParams* hParams = nullptr;   size_t hParamsCap = 0;
   uint8_t*     hOut = nullptr;      size_t hOutCap = 0;
+  int*         hFlagged = nullptr;  size_t hFlaggedCap = 0;
+  int32_t*     hHist = nullptr;     size_t hHistCap = 0;
 
   ~Instance() { release(); }
 
   void release()
   {
-    if (stream || dFrames || dParams || dAcc || dOut || hParams || hOut)
+    if (stream || dFrames || dParams || dAcc || dOut || hParams || hOut || dMxnTable)
       cudaSetDevice(device);
     if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); stream = nullptr; }
     cudaFree(dFrames); dFrames = nullptr; dFramesCap = 0;
     cudaFree(dParams); dParams = nullptr; dParamsCap = 0;
     cudaFree(dAcc);    dAcc = nullptr;    dAccCap = 0;
     cudaFree(dOut);    dOut = nullptr;    dOutCap = 0;
-    cudaFreeHost(hParams); hParams = nullptr; hParamsCap = 0;
-    cudaFreeHost(hOut);    hOut = nullptr;    hOutCap = 0;
+    cudaFree(dMxnTable); dMxnTable = nullptr;
+    cudaFree(dBitmaps);  dBitmaps = nullptr;  dBitmapsCap = 0;
+    cudaFree(dClusters); dClusters = nullptr; dClustersCap = 0;
+    cudaFree(dEqual);    dEqual = nullptr;    dEqualCap = 0;
+    cudaFree(dFlagged);  dFlagged = nullptr;  dFlaggedCap = 0;
+    cudaFree(dHist);     dHist = nullptr;     dHistCap = 0;
+    cudaFreeHost(hParams);  hParams = nullptr;  hParamsCap = 0;
+    cudaFreeHost(hOut);     hOut = nullptr;     hOutCap = 0;
+    cudaFreeHost(hFlagged); hFlagged = nullptr; hFlaggedCap = 0;
+    cudaFreeHost(hHist);    hHist = nullptr;    hHistCap = 0;
   }
 
   bool init_device()
@@ -142,6 +160,13 @@ struct Instance {
     device = dev;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (kind == KIND_OM)
+    {
+      uint32_t table[512];
+      mxn_color_table(table);
+      CUDA_TRY(cudaMalloc(&dMxnTable, sizeof(table)));
+      CUDA_TRY(cudaMemcpy(dMxnTable, table, sizeof(table), cudaMemcpyHostToDevice));
+    }
     return true;
   }
 
@@ -160,7 +185,11 @@ struct Instance {
     T* np = nullptr;
     CUDA_TRY(cudaMalloc(&np, ncap * sizeof(T)));
     if (zero)
+    {
+      // complete before returning: the buffer may be used on a caller's stream next
       CUDA_TRY(cudaMemsetAsync(np, 0, ncap * sizeof(T), stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+    }
     if (p)
     {
       CUDA_TRY(cudaStreamSynchronize(stream));
@@ -197,6 +226,10 @@ bool instance_setup(Instance* in, int width, int height, int lineLength, int out
   in->state = CarriedState();
   if (width < 0 || height < 0 || width % 32 != 0 || height % 4 != 0)
     return false;
+  // OO: bitmap row offsets and labels are uint16 in the reference (cv_bitmap_builder_reference.hpp:93-96);
+  // sizes where they would wrap are outside what it supports and are refused here
+  if (in->kind == KIND_OO && (long long)(width / 4) * (height / 4) > 65536LL)
+    return false;
   in->geo.width = width;
   in->geo.height = height;
   in->geo.lineLength = lineLength;
@@ -214,14 +247,34 @@ struct BatchView {
   const uint8_t* frames; int64_t frameStride; bool framesOnDevice;
   const uint8_t* inArgs; int inStride;
   uint8_t*       outArgs; int outStride; bool outOnDevice;
-  const int64_t* seeds;
+  const int64_t* seeds; bool seedsBroadcast;
   cudaStream_t   stream;
   bool           async;
 };
 
+size_t result_record_bytes(int kind)
+{
+  switch (kind)
+  {
+    case KIND_OO: return 36;
+    case KIND_OM: return 400;
+    default:      return sizeof(TargetOut);
+  }
+}
+
+bool wants_autodetect(int kind, const void* inArgsAlg)
+{
+  switch (kind)
+  {
+    case KIND_OO: return reinterpret_cast<const TRIKB200_ObjInArgsAlg*>(inArgsAlg)->autoDetectHsv != 0;
+    case KIND_OM: return false;
+    default:      return reinterpret_cast<const TRIKB200_RangeInArgsAlg*>(inArgsAlg)->autoDetectHsv != 0;
+  }
+}
+
 // merge a device result record into the caller's OutArgsAlg, touching only the fields the
 // reference's run() assigns for this call
-void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, uint8_t* dst)
+void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, const uint16_t* detect, uint8_t* dst)
 {
   switch (kind)
   {
@@ -229,14 +282,41 @@ void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, uint8_t* 
     {
       const TargetOut* r = reinterpret_cast<const TargetOut*>(rec);
       TRIKB200_TargetOutArgsAlg* o = reinterpret_cast<TRIKB200_TargetOutArgsAlg*>(dst);
-      const TRIKB200_RangeInArgsAlg* ia = reinterpret_cast<const TRIKB200_RangeInArgsAlg*>(inArgsAlg);
       o->targetX = r->targetX; o->targetY = r->targetY; o->targetSize = r->targetSize;
-      if (ia->autoDetectHsv)
+      if (wants_autodetect(kind, inArgsAlg))
       {
-        o->detectHue = r->detectHue; o->detectHueTolerance = r->detectHueTolerance;
-        o->detectSat = r->detectSat; o->detectSatTolerance = r->detectSatTolerance;
-        o->detectVal = r->detectVal; o->detectValTolerance = r->detectValTolerance;
+        if (detect)
+        {
+          o->detectHue = detect[0]; o->detectHueTolerance = detect[1];
+          o->detectSat = detect[2]; o->detectSatTolerance = detect[3];
+          o->detectVal = detect[4]; o->detectValTolerance = detect[5];
+        }
+        else
+        {
+          o->detectHue = r->detectHue; o->detectHueTolerance = r->detectHueTolerance;
+          o->detectSat = r->detectSat; o->detectSatTolerance = r->detectSatTolerance;
+          o->detectVal = r->detectVal; o->detectValTolerance = r->detectValTolerance;
+        }
       }
+      break;
+    }
+    case KIND_OO:
+    {
+      TRIKB200_ObjOutArgsAlg* o = reinterpret_cast<TRIKB200_ObjOutArgsAlg*>(dst);
+      memcpy(o->target, rec, sizeof(o->target));           // memset + fill of all eight (cv_ball_detector_seqpass.hpp:569-597)
+      if (detect && wants_autodetect(kind, inArgsAlg))
+      {
+        o->detectHue = detect[0]; o->detectHueTolerance = detect[1];
+        o->detectSat = detect[2]; o->detectSatTolerance = detect[3];
+        o->detectVal = detect[4]; o->detectValTolerance = detect[5];
+      }
+      break;
+    }
+    case KIND_OM:
+    {
+      const TRIKB200_MxnInArgsAlg* ia = reinterpret_cast<const TRIKB200_MxnInArgsAlg*>(inArgsAlg);
+      const int cells = (int)(uint8_t)ia->widthM * (int)(uint8_t)ia->heightN;
+      memcpy(dst, rec, sizeof(int32_t) * (size_t)cells);   // only counter entries are assigned (:605-618)
       break;
     }
     default:
@@ -252,15 +332,41 @@ bool run_batch(Instance* in, const BatchView& b)
     return false;
   }
   const int kind = in->kind;
-  if (kind != KIND_WO && kind != KIND_WL && kind != KIND_OL)
-  {
-    set_error("sensor kind not available in this build");
-    return false;
-  }
   CUDA_TRY(cudaSetDevice(in->device));
   cudaStream_t s = b.stream ? b.stream : in->stream;
   const size_t fbytes = in->frame_bytes();
-  const size_t recBytes = sizeof(TargetOut);
+  const size_t recBytes = result_record_bytes(kind);
+  const size_t inSize = in_args_alg_size(kind);
+
+  // 0. argument checks that the reference leaves to undefined behaviour
+  int maxRows = 0, maxCols = 0, numFlagged = 0;
+  const size_t nargs = (b.inStride == 0) ? 1 : (size_t)b.n;
+  for (size_t i = 0; i < nargs; ++i)
+  {
+    const uint8_t* ia = b.inArgs + i * (size_t)b.inStride;
+    if (kind == KIND_OM)
+    {
+      const TRIKB200_MxnInArgsAlg* a = reinterpret_cast<const TRIKB200_MxnInArgsAlg*>(ia);
+      const int M = (uint8_t)a->widthM, N = (uint8_t)a->heightN;
+      if (M == 0 || N == 0 || M * N > 100)
+      {
+        // the reference divides by zero / overruns outColor[100] (mxn_sensor/.../cv_ball_detector_seqpass.hpp:587-588,612)
+        set_error("mxn sensor: widthM and heightN must be >= 1 with widthM*heightN <= 100");
+        return false;
+      }
+      if (M > maxRows) maxRows = M;
+      if (N > maxCols) maxCols = N;
+    }
+    else if (wants_autodetect(kind, ia))
+      numFlagged += (b.inStride == 0) ? b.n : 1;
+  }
+  const bool hostTail = numFlagged > 0 && kind != KIND_WO;
+  if (hostTail && (b.async || b.outOnDevice))
+  {
+    set_error("annealed auto-detect needs its host tail: not available with TRIKB200_BATCH_ASYNC or device results");
+    return false;
+  }
+  (void)inSize;
 
   // 1. per-frame parameters (carried state advances frame by frame, as n process() calls would)
   const bool broadcast = (b.inStride == 0) && kind != KIND_OL && kind != KIND_OO;
@@ -288,20 +394,68 @@ bool run_batch(Instance* in, const BatchView& b)
     g.frameStride = (int64_t)stride;
   }
 
-  // 3. kernels
-  if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
+  // 3. the per-pixel kernels
   uint8_t* dOut;
-  if (b.outOnDevice && b.outStride == (int)recBytes)
+  const bool directOut = b.outOnDevice && b.outStride == (int)recBytes && kind != KIND_OM;
+  if (directOut)
     dOut = b.outArgs;
   else
   {
     if (!in->grow_device(in->dOut, in->dOutCap, recBytes * b.n, false)) return false;
     dOut = in->dOut;
   }
-  CUDA_TRY(launch_sum_sensor(kind, g, b.n, dFrames, in->dParams, broadcast ? 0 : 1, in->dAcc,
-                             reinterpret_cast<TargetOut*>(dOut), g_slabsPerFrame, s));
+  const int pstride = broadcast ? 0 : 1;
+  switch (kind)
+  {
+    case KIND_WO: case KIND_WL: case KIND_OL:
+      if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
+      CUDA_TRY(launch_sum_sensor(kind, g, b.n, dFrames, in->dParams, pstride, in->dAcc,
+                                 reinterpret_cast<TargetOut*>(dOut), g_slabsPerFrame, s));
+      break;
+    case KIND_OM:
+      if (b.outOnDevice)
+        CUDA_TRY(cudaMemsetAsync(dOut, 0, recBytes * b.n, s));
+      CUDA_TRY(launch_om(g, b.n, dFrames, in->dParams, pstride, in->dMxnTable, reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s));
+      break;
+    case KIND_OO:
+    {
+      const size_t cells = (size_t)(g.width / 4) * (g.height / 4);
+      const int maxLabels = oo_max_labels(g.width, g.height);
+      if (!in->grow_device(in->dBitmaps, in->dBitmapsCap, cells * b.n, false)) return false;
+      if (!in->grow_device(in->dClusters, in->dClustersCap, (size_t)12 * maxLabels * b.n, false)) return false;
+      if (!in->grow_device(in->dEqual, in->dEqualCap, (size_t)maxLabels * b.n, false)) return false;
+      CUDA_TRY(launch_oo(g, b.n, dFrames, in->dParams, pstride, in->dBitmaps, in->dClusters, in->dEqual, maxLabels, dOut, nullptr, s));
+      break;
+    }
+    default:
+      set_error("unknown sensor kind");
+      return false;
+  }
 
-  // 4. results
+  // 4. auto-calibration histograms for the frames that ask for it
+  const int histBins = (kind == KIND_OO) ? 1024 : 256;
+  if (numFlagged > 0)
+  {
+    if (!in->grow_pinned(in->hFlagged, in->hFlaggedCap, (size_t)numFlagged)) return false;
+    if (!in->grow_device(in->dFlagged, in->dFlaggedCap, (size_t)numFlagged, false)) return false;
+    int k = 0;
+    for (int i = 0; i < b.n; ++i)
+      if (wants_autodetect(kind, b.inArgs + (size_t)i * b.inStride))
+        in->hFlagged[k++] = i;
+    CUDA_TRY(cudaMemcpyAsync(in->dFlagged, in->hFlagged, sizeof(int) * numFlagged, cudaMemcpyHostToDevice, s));
+    if (kind == KIND_WO)
+      CUDA_TRY(launch_wo_detect(g, numFlagged, dFrames, in->dFlagged, reinterpret_cast<TargetOut*>(dOut), s));
+    else
+    {
+      const size_t words = (size_t)(histBins + 2) * numFlagged;
+      if (!in->grow_device(in->dHist, in->dHistCap, words, false)) return false;
+      if (!in->grow_pinned(in->hHist, in->hHistCap, words)) return false;
+      CUDA_TRY(launch_ordered_hist(kind, g, numFlagged, dFrames, in->dFlagged, in->dHist, s));
+      CUDA_TRY(cudaMemcpyAsync(in->hHist, in->dHist, words * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+  }
+
+  // 5. results
   if (b.outOnDevice)
   {
     if (dOut != b.outArgs)
@@ -319,8 +473,44 @@ bool run_batch(Instance* in, const BatchView& b)
   if (!in->grow_pinned(in->hOut, in->hOutCap, recBytes * b.n)) return false;
   CUDA_TRY(cudaMemcpyAsync(in->hOut, dOut, recBytes * b.n, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+
+  // 6. host tail: anneal the flagged frames (threads across frames), then merge
+  std::vector<uint16_t> detect;
+  if (hostTail)
+  {
+    detect.assign((size_t)6 * numFlagged, 0);
+    const int nthreads = std::max(1, std::min<int>(numFlagged, (int)std::thread::hardware_concurrency()));
+    auto work = [&](int tid)
+    {
+      for (int k = tid; k < numFlagged; k += nthreads)
+      {
+        const int32_t* rec = in->hHist + (size_t)k * (histBins + 2);
+        const int frame = in->hFlagged[k];
+        const unsigned seed = (unsigned)(b.seeds ? b.seeds[b.seedsBroadcast ? 0 : frame] : (int64_t)time(NULL));
+        if (kind == KIND_OO)
+          anneal_oo(rec, rec[histBins], seed, &detect[(size_t)6 * k]);
+        else
+          anneal_line(rec, rec[histBins], kind == KIND_OL, seed, &detect[(size_t)6 * k]);
+      }
+    };
+    if (nthreads == 1)
+      work(0);
+    else
+    {
+      std::vector<std::thread> pool;
+      for (int tIdx = 0; tIdx < nthreads; ++tIdx) pool.emplace_back(work, tIdx);
+      for (auto& th : pool) th.join();
+    }
+  }
+  int k = 0;
   for (int i = 0; i < b.n; ++i)
-    merge_result(kind, b.inArgs + (size_t)i * b.inStride, in->hOut + (size_t)i * recBytes, b.outArgs + (size_t)i * b.outStride);
+  {
+    const uint8_t* ia = b.inArgs + (size_t)i * b.inStride;
+    const uint16_t* det = nullptr;
+    if (hostTail && wants_autodetect(kind, ia))
+      det = &detect[(size_t)6 * k++];
+    merge_result(kind, ia, in->hOut + (size_t)i * recBytes, det, b.outArgs + (size_t)i * b.outStride);
+  }
   return true;
 }
 
@@ -536,7 +726,7 @@ XDAS_Int32 vid_process(int kind, IVIDTRANSCODE_Handle algHandle, XDM1_BufDesc* i
       b.inArgs = inAlg; b.inStride = (int)in_args_alg_size(kind);
       b.outArgs = outAlg; b.outStride = (int)out_args_alg_size(kind); b.outOnDevice = false;
       int64_t seed = in->seed >= 0 ? in->seed : (int64_t)time(NULL);
-      b.seeds = &seed;
+      b.seeds = &seed; b.seedsBroadcast = true;
       b.stream = nullptr; b.async = false;
       ok = run_batch(in, b);
     }
@@ -791,7 +981,7 @@ XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Bat
   b.outArgs = reinterpret_cast<uint8_t*>(batch->outArgsAlg);
   b.outStride = batch->outArgsStride;
   b.outOnDevice = (batch->outArgsMem == TRIKB200_MEM_DEVICE);
-  b.seeds = batch->seeds;
+  b.seeds = batch->seeds; b.seedsBroadcast = false;
   b.stream = reinterpret_cast<cudaStream_t>(batch->stream);
   b.async = (batch->flags & TRIKB200_BATCH_ASYNC) != 0;
   return run_batch(in, b) ? IVIDTRANSCODE_EOK : IVIDTRANSCODE_EFAIL;

@@ -1,6 +1,7 @@
 // trik_host.cpp -- see trik_host.hpp.
 #include "trik_host.hpp"
 
+#include <cmath>
 #include <cstring>
 
 namespace trikb200 {
@@ -138,6 +139,42 @@ void prepare_frame_params(int kind, const Geometry& g, const void* inArgsAlg, Ca
   }
 }
 
+// float divisions widened to double, v < 0.2 -> 0, s < 0.2 -> 0 else 1, six-sector conversion,
+// truncation to int -- the arithmetic of HSVtoRGB() as written; plain IEEE, no libm.
+static uint32_t mxn_hsv_to_rgb(int H, int S, int V)
+{
+  double r = 0, g = 0, b = 0;
+  const double h = H / 255.0f;
+  double s = S / 255.0f;
+  double v = V / 255.0f;
+  v = v < 0.2 ? 0 : v;
+  s = s < 0.2 ? 0 : 1;
+  const int i = (int)(h * 6);
+  const double f = h * 6 - i;
+  const double p = v * (1 - s);
+  const double q = v * (1 - f * s);
+  const double t = v * (1 - (1 - f) * s);
+  switch (i % 6)
+  {
+    case 0: r = v; g = t; b = p; break;
+    case 1: r = q; g = v; b = p; break;
+    case 2: r = p; g = v; b = t; break;
+    case 3: r = p; g = q; b = v; break;
+    case 4: r = t; g = p; b = v; break;
+    case 5: r = v; g = p; b = q; break;
+  }
+  const int ri = (int)(r * 255), gi = (int)(g * 255), bi = (int)(b * 255);
+  return (uint32_t)((ri << 16) + (gi << 8) + bi);
+}
+
+void mxn_color_table(uint32_t table[512])
+{
+  for (int h = 0; h < 32; ++h)
+    for (int s = 0; s < 4; ++s)
+      for (int v = 0; v < 4; ++v)
+        table[(h << 4) | (s << 2) | v] = mxn_hsv_to_rgb(h * 8, s * 64, v * 64);
+}
+
 // glibc 2.39 stdlib/random_r.c, TYPE_3: degree 31, separation 3.
 void GlibcRand::seed(unsigned s)
 {
@@ -163,6 +200,153 @@ int GlibcRand::next()
   if (++f >= 31) f = 0;
   if (++b >= 31) b = 0;
   return (int)(val >> 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// annealing tails
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+const double kTEnd = 0.0005, kLambda = 0.76, kE = 2.718281828;
+const double kRandMax = 2147483647.0;                      // glibc RAND_MAX
+
+// do_getIncrement (WL/.../cv_hsv_range_detector.hpp:95-112): rejection sampling, inclusive bounds
+int line_increment(GlibcRand& rng, int val, int mn, int mx, double base, double t)
+{
+  for (;;)
+  {
+    if (mn == mx)
+      return mn;
+    const double alpha = rng.next() / kRandMax;
+    const double degree = 2 * alpha - 1;
+    const int res = (int)(val + ((std::pow(base, degree) - 1) * t) * (double)(mx - mn));
+    if (!((res < mn) || (res > mx)))
+      return res;
+  }
+}
+
+int64_t line_F(const int32_t* h, uint8_t v0, uint8_t v1)  // :133-159, empty bin = -K0 = -1
+{
+  int64_t res = 0;
+  for (int v = v0; v <= v1; v++)
+    res += h[v] != 0 ? h[v] : -1;
+  return res;
+}
+
+// getIncrement (OO/.../cv_hsv_range_detector.hpp:77-98): half-open upper bound
+int oo_increment(GlibcRand& rng, int val, int mn, int mx, double t)
+{
+  for (;;)
+  {
+    if (mn == mx)
+      return mn;
+    const double base = 1 + 1 / t;
+    const double alpha = rng.next() / kRandMax;
+    const double degree = 2 * alpha - 1;
+    const int res = (int)(val + ((std::pow(base, degree) - 1) * t) * (double)(mx - mn));
+    if ((mn <= res) && (res < mx))
+      return res;
+  }
+}
+
+int oo_truncate_hue(int v) { int r = v % 32; if (r < 0) r += 32; return r; }
+
+int64_t oo_foo(const int32_t* hs, int h1, int h2, int s1, int s2)   // m_foo :109-153, empty cell = -K0 = -2
+{
+  int64_t res = 0;
+  if (h1 <= h2)
+  {
+    for (int h = h1; h <= h2; h++)
+      for (int s = s1; s <= s2; s++)
+        res += hs[h * 32 + s] != 0 ? hs[h * 32 + s] : -2;
+  }
+  else
+  {
+    for (int h = h1; h < 32; h++)
+      for (int s = s1; s <= s2; s++)
+        res += hs[h * 32 + s] != 0 ? hs[h * 32 + s] : -2;
+    for (int h = 0; h <= h2; h++)
+      for (int s = s1; s <= s2; s++)
+        res += hs[h * 32 + s] != 0 ? hs[h * 32 + s] : -2;
+  }
+  return res;
+}
+
+} // namespace
+
+void anneal_line(const int32_t hist[256], int seedBin, bool isOL, unsigned seed, uint16_t out[6])
+{
+  GlibcRand rng;
+  rng.seed(seed);
+  uint8_t v0 = (uint8_t)seedBin, v1 = (uint8_t)seedBin;
+  int64_t L = line_F(hist, v0, v1);
+  double T = 150;
+  while (T > kTEnd)
+  {
+    for (int i = 0; i < 200; i++)
+    {
+      const double base = 1 + 1 / T;
+      const uint8_t n0 = (uint8_t)line_increment(rng, v0, 0, 255, base, T);
+      const uint8_t n1 = (uint8_t)line_increment(rng, v1, 0, 255, base, T);
+      const int64_t newL = line_F(hist, n0, n1);
+      if (rng.next() <= std::pow(kE, (newL - L) / T) * kRandMax)
+      {
+        v0 = n0; v1 = n1; L = newL;
+      }
+    }
+    T *= kLambda;
+  }
+  v0 = (uint8_t)((v0 << 0) * 0.39f);
+  v1 = isOL ? (uint8_t)((((v1 + 1) << 0)) * 0.39f) : (uint8_t)((((v1 + 1) << 0) - 1) * 0.39f);
+  out[0] = 0; out[1] = 0; out[2] = 0; out[3] = 0;
+  out[4] = (uint16_t)((v1 + v0) / 2);
+  out[5] = (uint16_t)((v1 - v0) / 2);
+}
+
+void anneal_oo(const int32_t hs[1024], int seedBin, unsigned seed, uint16_t out[6])
+{
+  GlibcRand rng;
+  rng.seed(seed);
+  const int sMax = seedBin & 31;
+  int h1 = seedBin >> 5, h2 = seedBin >> 5, s1 = sMax, s2 = sMax;
+  int64_t L = oo_foo(hs, h1, h2, s1, s2);
+  double T = 150;
+  while (T > kTEnd)
+  {
+    for (int i = 0; i < 200; i++)
+    {
+      const int h1n = oo_truncate_hue(oo_increment(rng, h1, 0, 32, T));
+      const int h2n = oo_truncate_hue(oo_increment(rng, h2, 0, 32, T));
+      const int s1n = oo_increment(rng, s1, 0, sMax, T);
+      const int s2n = oo_increment(rng, s2, sMax, 32, T);
+      const int64_t Ln = oo_foo(hs, h1n, h2n, s1n, s2n);
+      if (L < Ln || (rng.next() / kRandMax) <= std::pow(kE, -(L - Ln) / T))
+      {
+        h1 = h1n; h2 = h2n; s1 = s1n; s2 = s2n; L = Ln;
+      }
+    }
+    T *= kLambda;
+  }
+  h1 = (int)((h1 << 3) * 1.4f);
+  h2 = (int)((((h2 + 1) << 3) - 1) * 1.4f);
+  s1 = (int)((s1 << 3) * 0.39f);
+  s2 = (int)((((s2 + 1) << 3)) * 0.39f);
+  if (h1 <= h2)
+  {
+    out[0] = (uint16_t)((h2 + h1) / 2);
+    out[1] = (uint16_t)((h2 - h1) / 2);
+  }
+  else
+  {
+    const float hue = (h2 - (360.0f - h1)) / 2;
+    const float hueTolerance = (h2 + (360.0f - h1)) / 2;
+    out[0] = (uint16_t)(hue >= 0 ? hue : (hue + 360));
+    out[1] = (uint16_t)hueTolerance;
+  }
+  out[2] = (uint16_t)((s2 + s1) / 2);
+  out[3] = (uint16_t)((s2 - s1) / 2 + 2);
+  out[4] = 50;
+  out[5] = 50;
 }
 
 } // namespace trikb200

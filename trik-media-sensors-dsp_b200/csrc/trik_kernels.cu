@@ -20,7 +20,9 @@
 namespace trikb200 {
 
 static long long g_launches = 0;
-long long launch_count() { return g_launches; }
+extern long long g_launches_grid;
+extern long long g_launches_detect;
+long long launch_count() { return g_launches + g_launches_grid + g_launches_detect; }
 
 // ---------------------------------------------------------------------------------------------
 // per-pair work
@@ -114,7 +116,6 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
   __shared__ uint16_t s_lut43[256];
   __shared__ uint16_t s_lut255[256];
   __shared__ uint32_t s_red[32][4];
-  __shared__ bool s_last;
 
   const int frame = blockIdx.x / slabs;
   const int slab  = blockIdx.x - frame * slabs;
@@ -268,7 +269,6 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
         finalize_sum<KIND>(g, p, a, b, c, d, out + frame);
     }
   }
-  (void)s_last;
 }
 
 int sum_sensor_block_threads(int kind, int width)

@@ -58,6 +58,25 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
                               const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,
                               int slabsPerFrame, cudaStream_t stream);
 
+// OM: out = numFrames x int32[100] (only gridRows*gridCols entries per frame are written)
+cudaError_t launch_om(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
+                      int paramStride, const uint32_t* colorTable, int32_t* out, int maxGridRows, int maxGridCols,
+                      cudaStream_t stream);
+// OO: bitmaps = numFrames x (W/4)(H/4) uint16; clusters = numFrames x maxLabels x 12 bytes;
+// equal = numFrames x maxLabels uint16; out = numFrames x 36-byte ObjOutArgsAlg records
+cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
+                      int paramStride, uint16_t* bitmaps, void* clusters, uint16_t* equal, int maxLabels,
+                      void* out, int* labelCounts, cudaStream_t stream);
+inline int oo_max_labels(int width, int height) { return ((width / 4) / 2 + 1) * ((height / 4) / 2 + 1) + 2; }
+
+// auto-calibration histograms over the frames listed in frameIdx (device array of numFlagged indices)
+cudaError_t launch_wo_detect(const Geometry& g, int numFlagged, const uint8_t* frames, const int* frameIdx,
+                             TargetOut* out, cudaStream_t stream);
+// results: numFlagged records of (bins + 2) int32: the +1/-2 histogram, the seed bin, the seed value
+// (bins = 256 for WL/OL, 1024 = 32x32 (H>>3, S>>3) for OO)
+cudaError_t launch_ordered_hist(int kind, const Geometry& g, int numFlagged, const uint8_t* frames, const int* frameIdx,
+                                int32_t* results, cudaStream_t stream);
+
 // exhaustive pixel-function probes for the parity tests: out[i] for i = blockIdx*blockDim+threadIdx
 cudaError_t launch_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
 cudaError_t launch_probe_rgb2hsv(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);

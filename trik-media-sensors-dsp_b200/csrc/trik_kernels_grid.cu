@@ -1,0 +1,540 @@
+// trik_kernels_grid.cu -- the ov7670 mxn grid-colour sensor (OM) and the ov7670 object sensor (OO).
+//
+// OM  ov7670/mxn_sensor/include/internal/cv_ball_detector_seqpass.hpp
+//       pass 1 :252-296, GetImgColor2 :411-452, HSVtoRGB :480-517, grid loop :585-618
+//     Per cell the reference builds a 32x4x4 histogram of (H>>3, S>>6, V>>6) in raster order and
+//     keeps "the first bin to reach the final maximum".  For a pure counting histogram that is:
+//     among the bins whose final count equals the maximum, the one whose LAST pixel comes first.
+//     So the kernel keeps (count, last raster position) per bin -- atomicAdd + atomicMax in shared
+//     memory -- and the order of the additions no longer matters.
+//
+// OO  ov7670/object_sensor/include/internal/
+//       cv_bitmap_builder_reference.hpp:107-217  threshold -> 4x4 "metapixel" bitmap
+//       cv_clusterizer_reference.hpp:38-202      raster labelling with a one-level equivalence table
+//       cv_ball_detector_seqpass.hpp:569-597     the eight largest clusters -> targets
+//     The labelling is order dependent by construction (non-transitive equivalences, the first
+//     pixel of a label is not counted, merge in label order, std::sort tie order), so it is
+//     replayed step for step by one lane per frame; frames run in parallel.
+#include "trik_kernels.cuh"
+#include "trik_pixel.cuh"
+
+namespace trikb200 {
+
+extern long long g_launches_grid;
+long long g_launches_grid = 0;
+
+// =============================================================================================
+// OM
+// =============================================================================================
+constexpr int OM_BINS = 512;
+constexpr int OM_MAX_GROUP = 12;      // cells of one cell-row whose histograms live in shared memory at once
+
+__global__ void __launch_bounds__(1024)
+om_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+          const int paramStride, const uint32_t* __restrict__ colorTable, int32_t* __restrict__ out,
+          const int maxGridRows, const int cpr, const int rpi)
+{
+  extern __shared__ uint32_t s_dyn[];                     // [group][512] counts, then [group][512] last positions
+  __shared__ uint16_t s_lut43[256];
+  __shared__ uint16_t s_lut255[256];
+  __shared__ unsigned long long s_best[32];
+  __shared__ uint32_t s_bestBin[32];
+
+  const int frame = blockIdx.x / maxGridRows;
+  const int cellRow = blockIdx.x - frame * maxGridRows;
+  const FrameParams p = params[(size_t)frame * paramStride];
+  const int M = (int)p.gridRows, N = (int)p.gridCols;
+  if (cellRow >= M || N <= 0)
+    return;                                               // uniform per CTA
+  fill_div_luts(s_lut43, s_lut255);
+
+  const int W = g.width, H = g.height;
+  const int ws = W / N, hs = H / M;                       // m_widthStep, m_heightStep (:587-588); remainders ignored
+  const int t = threadIdx.x;
+  const int cc = t % cpr, rr = t / cpr;
+  const int col0 = cc * 16;
+  const int r0 = cellRow * hs, r1 = r0 + hs;
+  const int group = N < OM_MAX_GROUP ? N : OM_MAX_GROUP;
+  uint32_t* s_cnt = s_dyn;
+  uint32_t* s_pos = s_dyn + group * OM_BINS;
+
+  const uint8_t* base = frames + (size_t)frame * g.frameStride + (size_t)col0;
+  const size_t chromaOfs = (size_t)H * g.lineLength;
+  int32_t* frameOut = out + (size_t)frame * 100;
+
+  for (int g0 = 0; g0 < N; g0 += group)
+  {
+    const int g1 = min(g0 + group, N);
+    __syncthreads();
+    for (int i = t; i < 2 * group * OM_BINS; i += blockDim.x)
+      s_dyn[i] = 0u;
+    __syncthreads();
+
+    // does this thread's 16-pixel chunk touch the columns of cells g0..g1-1 ?
+    const int cLo = g0 * ws, cHi = g1 * ws;               // [cLo, cHi)
+    if (ws > 0 && col0 < cHi && col0 + 16 > cLo)
+    {
+      for (int row = r0 + rr; row < r1; row += rpi)
+      {
+        const uint8_t* ptr = base + (size_t)row * g.lineLength;
+        const uint4 lu = ld_stream(ptr);
+        const uint4 ch = ld_stream(ptr + chromaOfs);
+        const uint32_t L[4] = {lu.x, lu.y, lu.z, lu.w};
+        const uint32_t Cw[4] = {ch.x, ch.y, ch.z, ch.w};
+        int pendIdx = -1;                                 // run-length compression of identical (cell, bin)
+        uint32_t pendCnt = 0, pendPos = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+          const uint32_t yy = __byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140);
+          uint32_t hsv[2];
+          hsv_pair(yy, Cw[k >> 1], (k & 1) ? coef_planar1() : coef_planar0(), s_lut43, s_lut255, hsv[0], hsv[1]);
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+          {
+            const int col = col0 + 2 * k + e;
+            if (col < cLo || col >= cHi)
+              continue;
+            const int cell = col / ws - g0;
+            const uint32_t bin = ((hsv[e] & 0xFFu) >> 3 << 4) | (((hsv[e] >> 8) & 0xFFu) >> 6 << 2) | ((hsv[e] >> 16) >> 6);
+            const int idx = cell * OM_BINS + (int)bin;
+            const uint32_t pos = (uint32_t)row * (uint32_t)W + (uint32_t)col;
+            if (idx == pendIdx)
+            {
+              ++pendCnt; pendPos = pos;
+            }
+            else
+            {
+              if (pendIdx >= 0)
+              {
+                atomicAdd(&s_cnt[pendIdx], pendCnt);
+                atomicMax(&s_pos[pendIdx], pendPos);
+              }
+              pendIdx = idx; pendCnt = 1; pendPos = pos;
+            }
+          }
+        }
+        if (pendIdx >= 0)
+        {
+          atomicAdd(&s_cnt[pendIdx], pendCnt);
+          atomicMax(&s_pos[pendIdx], pendPos);
+        }
+      }
+    }
+    __syncthreads();
+
+    // per cell: max count, ties -> earliest last position, full tie (empty cell) -> bin 0
+    for (int c = 0; c < g1 - g0; ++c)
+    {
+      unsigned long long best = 0ull;
+      uint32_t bestBin = 0xFFFFFFFFu;
+      for (int b = t; b < OM_BINS; b += blockDim.x)
+      {
+        const unsigned long long key = ((unsigned long long)s_cnt[c * OM_BINS + b] << 32)
+                                     | (unsigned long long)(0xFFFFFFFFu - s_pos[c * OM_BINS + b]);
+        if (key > best || (key == best && (uint32_t)b < bestBin))
+        {
+          best = key; bestBin = (uint32_t)b;
+        }
+      }
+      const unsigned am = __activemask();
+      for (int off = 16; off > 0; off >>= 1)
+      {
+        const unsigned long long ok = __shfl_down_sync(am, best, off);
+        const uint32_t ob = __shfl_down_sync(am, bestBin, off);
+        if (ok > best || (ok == best && ob < bestBin))
+        {
+          best = ok; bestBin = ob;
+        }
+      }
+      const int warp = t >> 5, lane = t & 31, nwarps = (blockDim.x + 31) >> 5;
+      if (lane == 0) { s_best[warp] = best; s_bestBin[warp] = bestBin; }
+      __syncthreads();
+      if (t == 0)
+      {
+        for (int w2 = 1; w2 < nwarps; ++w2)
+          if (s_best[w2] > best || (s_best[w2] == best && s_bestBin[w2] < bestBin))
+          {
+            best = s_best[w2]; bestBin = s_bestBin[w2];
+          }
+        if (bestBin >= (uint32_t)OM_BINS) bestBin = 0;
+        frameOut[cellRow * N + g0 + c] = (int32_t)colorTable[bestBin];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+cudaError_t launch_om(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
+                      int paramStride, const uint32_t* colorTable, int32_t* out, int maxGridRows, int maxGridCols,
+                      cudaStream_t stream)
+{
+  if (numFrames <= 0 || maxGridRows <= 0)
+    return cudaSuccess;
+  const int cpr = g.width / 16;
+  if (cpr <= 0 || cpr > 1024)
+    return cudaErrorInvalidValue;
+  int k = (256 + cpr - 1) / cpr;
+  if (cpr * k > 1024) k = 1024 / cpr;
+  const int threads = cpr * k;
+  const int group = maxGridCols < OM_MAX_GROUP ? maxGridCols : OM_MAX_GROUP;
+  const size_t smem = (size_t)2 * group * OM_BINS * sizeof(uint32_t);
+  const long long grid = (long long)numFrames * maxGridRows;
+  if (grid > 0x7FFFFFFFLL)
+    return cudaErrorInvalidValue;
+  cudaFuncSetAttribute(om_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * OM_MAX_GROUP * OM_BINS * (int)sizeof(uint32_t));
+  om_kernel<<<(unsigned)grid, threads, smem, stream>>>(g, frames, params, paramStride, colorTable, out, maxGridRows, cpr, k);
+  ++g_launches_grid;
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// OO, step 1: threshold -> metapixel bitmap
+// =============================================================================================
+// bitmap[(row/4) * (W/4) + col/4], bit (row%4)*4 + col%4 = det   (cv_bitmap_builder_reference.hpp:163-187)
+__global__ void __launch_bounds__(1024)
+oo_bitmap_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+                 const int paramStride, uint16_t* __restrict__ bitmaps, const int cpr, const int rpi)
+{
+  __shared__ uint16_t s_lut43[256];
+  __shared__ uint16_t s_lut255[256];
+  fill_div_luts(s_lut43, s_lut255);
+  __syncthreads();
+
+  const int slabs = gridDim.y;
+  const int frame = blockIdx.x;
+  const FrameParams p = params[(size_t)frame * paramStride];
+  const int t = threadIdx.x;
+  const int cc = t % cpr, rr = t / cpr;
+  const int bw = g.width / 4, bh = g.height / 4;
+  const int mrPerSlab = (bh + slabs - 1) / slabs;
+  const int mr0 = blockIdx.y * mrPerSlab, mr1 = min(mr0 + mrPerSlab, bh);
+  const uint8_t* base = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u;
+  const size_t chromaOfs = (size_t)g.height * g.lineLength;
+  uint16_t* bm = bitmaps + (size_t)frame * bw * bh;
+
+  for (int mr = mr0 + rr; mr < mr1; mr += rpi)
+  {
+    uint32_t meta[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+      const uint8_t* ptr = base + (size_t)(mr * 4 + r) * g.lineLength;
+      const uint4 lu = ld_stream(ptr);
+      const uint4 ch = ld_stream(ptr + chromaOfs);
+      const uint32_t L[4] = {lu.x, lu.y, lu.z, lu.w};
+      const uint32_t Cw[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        const uint32_t yy = __byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140);
+        uint32_t h0, h1;
+        hsv_pair(yy, Cw[k >> 1], (k & 1) ? coef_planar1() : coef_planar0(), s_lut43, s_lut255, h0, h1);
+        const uint32_t d0 = detect_hsv(h0, p.from, p.to, p.expected) ? 1u : 0u;
+        const uint32_t d1 = detect_hsv(h1, p.from, p.to, p.expected) ? 1u : 0u;
+        meta[k >> 1] |= (d0 | (d1 << 1)) << (r * 4 + (k & 1) * 2);
+      }
+    }
+    uint2 v;
+    v.x = meta[0] | (meta[1] << 16);
+    v.y = meta[2] | (meta[3] << 16);
+    *reinterpret_cast<uint2*>(bm + (size_t)mr * bw + cc * 4) = v;
+  }
+}
+
+// =============================================================================================
+// OO, step 2: labelling + ranking + targets, one warp per frame, lane 0 sequences
+// =============================================================================================
+struct OoCluster { int32_t x, y, size; };
+
+// libstdc++ 13 std::sort (bits/stl_algo.h: __introsort_loop, __final_insertion_sort, _S_threshold = 16;
+// bits/stl_heap.h for the depth-limit fallback) with compareTargetBySize (cv_clusterizer_reference.hpp:28-31).
+// Restated because the order of equal sizes is observable in the eight reported targets.
+__device__ __forceinline__ bool oo_before(const OoCluster& a, const OoCluster& b) { return a.size > b.size; }
+__device__ __forceinline__ void oo_swap(OoCluster& a, OoCluster& b) { const OoCluster t = a; a = b; b = t; }
+
+__device__ void oo_push_heap(OoCluster* first, int hole, int top, OoCluster value)
+{
+  int parent = (hole - 1) / 2;
+  while (hole > top && oo_before(first[parent], value))
+  {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+__device__ void oo_adjust_heap(OoCluster* first, int hole, int len, OoCluster value)
+{
+  const int top = hole;
+  int second = hole;
+  while (second < (len - 1) / 2)
+  {
+    second = 2 * (second + 1);
+    if (oo_before(first[second], first[second - 1]))
+      second--;
+    first[hole] = first[second];
+    hole = second;
+  }
+  if ((len & 1) == 0 && second == (len - 2) / 2)
+  {
+    second = 2 * (second + 1);
+    first[hole] = first[second - 1];
+    hole = second - 1;
+  }
+  oo_push_heap(first, hole, top, value);
+}
+__device__ void oo_heap_sort(OoCluster* first, int len)
+{
+  if (len >= 2)
+    for (int parent = (len - 2) / 2;; --parent)
+    {
+      oo_adjust_heap(first, parent, len, first[parent]);
+      if (parent == 0)
+        break;
+    }
+  int last = len;
+  while (last > 1)
+  {
+    --last;
+    const OoCluster value = first[last];
+    first[last] = first[0];
+    oo_adjust_heap(first, 0, last, value);
+  }
+}
+__device__ void oo_linear_insert(OoCluster* a, int last)
+{
+  const OoCluster val = a[last];
+  int next = last - 1;
+  while (oo_before(val, a[next]))
+  {
+    a[last] = a[next];
+    last = next;
+    --next;
+  }
+  a[last] = val;
+}
+__device__ void oo_insertion_sort(OoCluster* a, int first, int last)
+{
+  if (first == last) return;
+  for (int i = first + 1; i != last; ++i)
+  {
+    if (oo_before(a[i], a[first]))
+    {
+      const OoCluster val = a[i];
+      for (int j = i; j > first; --j)
+        a[j] = a[j - 1];
+      a[first] = val;
+    }
+    else
+      oo_linear_insert(a, i);
+  }
+}
+__device__ void oo_std_sort(OoCluster* a, int n)
+{
+  if (n <= 0) return;
+  int lg = 0;
+  while ((n >> (lg + 1)) != 0) ++lg;
+  // __introsort_loop, recursion on the right part turned into an explicit stack
+  int stackFirst[64], stackLast[64], stackDepth[64];
+  int sp = 0;
+  stackFirst[0] = 0; stackLast[0] = n; stackDepth[0] = 2 * lg; sp = 1;
+  while (sp > 0)
+  {
+    --sp;
+    const int first = stackFirst[sp];
+    int last = stackLast[sp], depth = stackDepth[sp];
+    // the reference recursion runs introsort_loop(cut,last) to completion BEFORE continuing with
+    // [first,cut); the two ranges are disjoint, so the order of processing cannot change the result
+    while (last - first > 16)
+    {
+      if (depth == 0)
+      {
+        oo_heap_sort(a + first, last - first);
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      {                                                   // __move_median_to_first(first, first+1, mid, last-1)
+        OoCluster &r = a[first], &x = a[first + 1], &y = a[mid], &z = a[last - 1];
+        if (oo_before(x, y))
+        {
+          if (oo_before(y, z)) oo_swap(r, y);
+          else if (oo_before(x, z)) oo_swap(r, z);
+          else oo_swap(r, x);
+        }
+        else if (oo_before(x, z)) oo_swap(r, x);
+        else if (oo_before(y, z)) oo_swap(r, z);
+        else oo_swap(r, y);
+      }
+      int lo = first + 1, hi = last;                      // __unguarded_partition(first+1, last, pivot = first)
+      for (;;)
+      {
+        while (oo_before(a[lo], a[first])) ++lo;
+        --hi;
+        while (oo_before(a[first], a[hi])) --hi;
+        if (!(lo < hi))
+          break;
+        oo_swap(a[lo], a[hi]);
+        ++lo;
+      }
+      const int cut = lo;
+      if (sp < 64)
+      {
+        stackFirst[sp] = cut; stackLast[sp] = last; stackDepth[sp] = depth; ++sp;
+      }
+      last = cut;
+    }
+  }
+  if (n > 16)                                             // __final_insertion_sort
+  {
+    oo_insertion_sort(a, 0, 16);
+    for (int i = 16; i != n; ++i)
+      oo_linear_insert(a, i);
+  }
+  else
+    oo_insertion_sort(a, 0, n);
+}
+
+struct ObjOut {                                           // == TRIKB200_ObjOutArgsAlg (36 bytes)
+  int8_t  t[24];                                          // XDAS_Target target[8] = {int8 x, int8 y, uint8 size}
+  uint16_t detectHue, detectHueTolerance, detectSat, detectSatTolerance, detectVal, detectValTolerance;
+};
+static_assert(sizeof(ObjOut) == 36, "ObjOutArgsAlg layout");
+
+__global__ void __launch_bounds__(32)
+oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoCluster* __restrict__ clustersAll,
+                  uint16_t* __restrict__ equalAll, const int maxLabels, ObjOut* __restrict__ out, int* __restrict__ labelCounts)
+{
+  extern __shared__ uint16_t s_rows[];                    // two label rows of bw entries
+  const int frame = blockIdx.x;
+  const int bw = g.width / 4, bh = g.height / 4;
+  const uint16_t* bm = bitmaps + (size_t)frame * bw * bh;
+  OoCluster* cl = clustersAll + (size_t)frame * maxLabels;
+  uint16_t* eq = equalAll + (size_t)frame * maxLabels;
+  uint16_t* prev = s_rows;
+  uint16_t* cur = s_rows + bw;
+  for (int i = threadIdx.x; i < 2 * bw; i += 32)
+    s_rows[i] = 0;
+  __syncwarp();
+  if (threadIdx.x != 0)
+    return;
+
+  int ncl = 1;                                            // label 0 = background (:181-186)
+  eq[0] = 0;
+  cl[0] = OoCluster{0, 0, 0};
+  for (int row = 0; row < bh; ++row)
+  {
+    for (int col = 0; col < bw; ++col)
+    {
+      uint16_t lab = 0;
+      if (__popc((unsigned)bm[row * bw + col]) > 2)       // pop(...) > METAPIX_SIZE/2 (:192)
+      {
+        uint16_t a[4] = {0, 0, 0, 0};                     // left, up-left, up, up-right (:69-83)
+        if (row != 0)
+        {
+          a[2] = prev[col];
+          if (col != 0) a[1] = prev[col - 1];
+          if (col != bw - 1) a[3] = prev[col + 1];
+        }
+        if (col != 0) a[0] = cur[col - 1];
+        uint16_t v = a[0];                                // min(): smallest non-zero (:44-52)
+#pragma unroll
+        for (int n = 1; n < 4; ++n)
+          if ((a[n] < v && a[n] != 0) || v == 0)
+            v = a[n];
+        if (v)
+        {
+          lab = v;
+          cl[v].x += col; cl[v].y += row; cl[v].size += 1;
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if (a[n])
+              if (!(a[n] == v || eq[a[n]] == eq[v]))
+                eq[a[n]] = eq[v];
+        }
+        else if (ncl < maxLabels)
+        {
+          lab = (uint16_t)ncl;                            // a new label starts with ZERO mass (:104-111)
+          eq[ncl] = (uint16_t)ncl;
+          cl[ncl] = OoCluster{0, 0, 0};
+          ++ncl;
+        }
+      }
+      cur[col] = lab;
+    }
+    uint16_t* tmp = prev; prev = cur; cur = tmp;
+  }
+  for (int i = 0; i < ncl; ++i)                           // postProcessing (:115-124)
+  {
+    const int e = eq[i];
+    if (i != e)
+    {
+      cl[e].x += cl[i].x; cl[e].y += cl[i].y; cl[e].size += cl[i].size;
+      cl[i].size = 0;
+    }
+  }
+  oo_std_sort(cl, ncl);                                   // std::sort(..., compareTargetBySize) (:126)
+
+  ObjOut r;
+  for (int i = 0; i < 24; ++i) r.t[i] = 0;
+  r.detectHue = r.detectHueTolerance = r.detectSat = r.detectSatTolerance = r.detectVal = r.detectValTolerance = 0;
+  bool noObjects = true;
+  const int W = g.width, H = g.height;
+  for (int i = 0; i < 8; ++i)                             // cv_ball_detector_seqpass.hpp:572-590
+  {
+    // slots past the last label: the reference reads beyond its vector (undefined); defined here as empty
+    const OoCluster c = (i < ncl) ? cl[i] : OoCluster{0, 0, 0};
+    int size = (int)sqrtf((float)(uint16_t)c.size);
+    const uint32_t radius = (uint32_t)ceilf((float)size / 3.1415927f);
+    size = (int)((uint32_t)(radius * 100u * 4u) / (uint32_t)(bw + bh));
+    if (size > 4)
+    {
+      noObjects = false;
+      const int x = (c.x / (c.size + 1)) * 4;
+      const int y = (c.y / (c.size + 1)) * 4;
+      r.t[3 * i + 2] = (int8_t)(uint8_t)size;
+      r.t[3 * i + 0] = (int8_t)(((x - W / 2) * 100 * 2) / W);
+      r.t[3 * i + 1] = (int8_t)(((y - H / 2) * 100 * 2) / H);
+    }
+  }
+  if (noObjects)
+  {
+    r.t[0] = 0; r.t[1] = 0; r.t[2] = 0;
+  }
+  out[frame] = r;
+  if (labelCounts)
+    labelCounts[frame] = ncl;
+}
+
+cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
+                      int paramStride, uint16_t* bitmaps, void* clusters, uint16_t* equal, int maxLabels,
+                      void* out, int* labelCounts, cudaStream_t stream)
+{
+  if (numFrames <= 0)
+    return cudaSuccess;
+  const int cpr = g.width / 16;
+  if (cpr <= 0 || cpr > 1024)
+    return cudaErrorInvalidValue;
+  int k = (256 + cpr - 1) / cpr;
+  if (cpr * k > 1024) k = 1024 / cpr;
+  const int bh = g.height / 4;
+  int slabs = (148 * 8 + numFrames - 1) / numFrames;
+  const int maxSlabs = bh / (k * 2) > 0 ? bh / (k * 2) : 1;
+  if (slabs > maxSlabs) slabs = maxSlabs;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 65535) slabs = 65535;
+  dim3 grid((unsigned)numFrames, (unsigned)slabs);
+  oo_bitmap_kernel<<<grid, cpr * k, 0, stream>>>(g, frames, params, paramStride, bitmaps, cpr, k);
+  ++g_launches_grid;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return e;
+  const size_t smem = (size_t)2 * (g.width / 4) * sizeof(uint16_t);
+  oo_cluster_kernel<<<(unsigned)numFrames, 32, smem, stream>>>(g, bitmaps, reinterpret_cast<OoCluster*>(clusters), equal,
+                                                               maxLabels, reinterpret_cast<ObjOut*>(out), labelCounts);
+  ++g_launches_grid;
+  return cudaGetLastError();
+}
+
+} // namespace trikb200
