@@ -14,6 +14,10 @@ INC="-I$HERE/stubs -I$HERE/../include"
 CXXFLAGS="-std=gnu++11 $OPT -fPIC -DNDEBUG=1 -fno-strict-aliasing -Dtypeof=__typeof__ -w"
 CFLAGS="$OPT -fPIC -DNDEBUG=1 -w"
 
+declare -A CLASSES=([wo]=BallDetector [wl]=LineDetector [oo]=BallDetector [ol]=LineDetector [om]=BallDetector)
+declare -A FORMATS=([wo]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422 [wl]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422
+                    [oo]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P [ol]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P
+                    [om]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P)
 declare -A DIRS=(
   [wo]="$REF/trik/webcam/object_sensor"
   [wl]="$REF/trik/webcam/line_sensor"
@@ -41,7 +45,10 @@ for kind in "$@"; do
       > "$tmp/patch/internal/cv_bitmap_builder_reference.hpp"
     extra="-I$tmp/patch"
   fi
-  $CXX $CXXFLAGS $extra -I"$dir" -I"$dir/include" $INC -c "$dir/src/vidtranscode_cv.cpp" -o "$tmp/cv.o"
+  # ref_unit.cpp #includes the reference's src/vidtranscode_cv.cpp verbatim and adds the pixel probes
+  $CXX $CXXFLAGS $extra -I"$dir" -I"$dir/include" $INC \
+       -DTRIKREF_SRC="\"$dir/src/vidtranscode_cv.cpp\"" -DTRIKREF_CLASS="${CLASSES[$kind]}" -DTRIKREF_FORMAT="${FORMATS[$kind]}" \
+       -c "$HERE/ref_unit.cpp" -o "$tmp/cv.o"
   $CC  $CFLAGS -I"$dir" -I"$dir/include" $INC -c "$dir/src/vidtranscode_cv_fxns.c" -o "$tmp/fxns.o"
   $CC  $CFLAGS -Wall -I"$dir" -I"$dir/include" $INC -c "$HERE/ref_driver.c" -o "$tmp/drv.o"
   $CXX $OPT -shared -o "$OUT/libtrikref_${kind}${SUFFIX}.so" "$tmp/cv.o" "$tmp/fxns.o" "$tmp/drv.o" -Wl,--wrap=time -lm

@@ -102,6 +102,8 @@ class RefSensor:
         self.lib.trikref_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         self.lib.trikref_set_time.argtypes = [C.c_longlong]
+        self.lib.trikref_probe_yuv2rgb.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        self.lib.trikref_probe_rgb2hsv.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         self.lib.trikref_fxns.restype = C.c_void_p
         self.lib.trikref_handle.restype = C.c_void_p
         assert self.lib.trikref_sizeof_inargs_alg() == C.sizeof(IN_ARGS[kind]), "InArgsAlg layout"
@@ -166,6 +168,8 @@ def port_lib():
         lib.trik_oracle_rgb888_to_hsv.argtypes = [C.c_uint32]
         lib.trik_oracle_hsv_to_rgb_mxn.argtypes = [C.c_int] * 3
         lib.trik_oracle_detect.argtypes = [C.c_uint32] * 4
+        lib.trik_oracle_yuv_to_rgb888_range.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+        lib.trik_oracle_rgb888_to_hsv_range.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         lib.trik_oracle_srand.argtypes = [C.c_void_p, C.c_uint]
         lib.trik_oracle_rand.argtypes = [C.c_void_p]
         _port = lib

@@ -71,6 +71,23 @@ int trik_oracle_detect(uint32_t hsv, uint32_t from, uint32_t to, uint32_t expect
   return mask == expected;
 }
 
+void trik_oracle_yuv_to_rgb888_range(uint32_t first, uint32_t count, uint32_t* out)
+{
+  uint32_t i;
+  for (i = 0; i < count; ++i)
+  {
+    const uint32_t idx = first + i;                  /* Y | U << 8 | V << 16 */
+    out[i] = trik_oracle_yuv_to_rgb888(idx & 0xff, (idx >> 8) & 0xff, (idx >> 16) & 0xff);
+  }
+}
+
+void trik_oracle_rgb888_to_hsv_range(uint32_t first, uint32_t count, uint32_t* out)
+{
+  uint32_t i;
+  for (i = 0; i < count; ++i)
+    out[i] = trik_oracle_rgb888_to_hsv(first + i);
+}
+
 /* OM/inc/cv_ball_detector_seqpass.hpp:480-517.  float divisions promoted to double, as written. */
 uint32_t trik_oracle_hsv_to_rgb_mxn(int H, int S, int V)
 {

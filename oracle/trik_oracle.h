@@ -66,6 +66,9 @@ typedef struct trik_oracle_sensor trik_oracle_sensor;
 /* pixel functions (section 8 rows a4, a5, a6) */
 uint32_t trik_oracle_yuv_to_rgb888(uint32_t y, uint32_t u, uint32_t v);
 uint32_t trik_oracle_rgb888_to_hsv(uint32_t rgb888);
+/* bulk forms: index = Y | U<<8 | V<<16 -> 0x00RRGGBB ; index = 0x00RRGGBB -> 0x00VVSSHH */
+void     trik_oracle_yuv_to_rgb888_range(uint32_t first, uint32_t count, uint32_t* out);
+void     trik_oracle_rgb888_to_hsv_range(uint32_t first, uint32_t count, uint32_t* out);
 int      trik_oracle_detect(uint32_t hsv, uint32_t range_from, uint32_t range_to, uint32_t expected);
 uint32_t trik_oracle_hsv_to_rgb_mxn(int h, int s, int v);
 

@@ -707,10 +707,13 @@ XDAS_Int32 vid_process(int kind, IVIDTRANSCODE_Handle algHandle, XDM1_BufDesc* i
   bool ok = (in != nullptr) && in->valid;
   if (ok)
   {
-    // YUV422P reads two planes of height*lineLength bytes; the reference only checks one
-    // (ov7670/object_sensor/.../cv_ball_detector_seqpass.hpp:519) and reads past numBytes.  Here the whole
-    // frame must be inside numBytes (documented deviation, DESIGN.md "Boundary").
-    if ((long long)in->frame_bytes() > (long long)vidInArgs->numBytes)
+    // run() checks height*lineLength against numBytes (cv_ball_detector_seqpass.hpp:415-416) -- for
+    // YUV422P that covers the luma plane only although both planes are read (:345-349).  Same check
+    // here; additionally both planes must lie inside the caller's BUFFER (bufSize), the one case
+    // where the reference would read out of bounds (documented deviation, DESIGN.md "Boundary").
+    if ((long long)in->geo.height * in->geo.lineLength > (long long)vidInArgs->numBytes)
+      ok = false;
+    if ((long long)in->frame_bytes() > (long long)inBuf->bufSize)
       ok = false;
     if ((long long)in->outHeight * in->outLineLength > (long long)outSize)
       ok = false;

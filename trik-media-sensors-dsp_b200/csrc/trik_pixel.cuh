@@ -11,7 +11,8 @@
 //     VIMNMX.U16x2, VIMNMX3.U16x2) and a byte dot product (IDP.4A), which is everything the
 //     colour matrix needs.
 //   * The reference computes R,G,B as int16 sums that WRAP (only blue can: 129*U-17672+74*Y
-//     exceeds 32767 for 27136 of the 65536 (Y,U) pairs), then >>6 and saturates to 0..255.
+//     exceeds 32767 for 106 of the 65536 (Y,U) pairs, all with U >= 245), then >>6 and saturates
+//     to 0..255, so those pixels come out with B = 0 instead of 255.
 //     Here every lane holds key = (value + 0x8000) mod 2^16, so unsigned lane order equals the
 //     reference's signed order and the blue wrap is simply the lane wrap of VIADD.16x2.
 //     Red and green keys cannot overflow a lane (max 63400 / 60334), so their "replicate the

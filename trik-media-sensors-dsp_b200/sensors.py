@@ -109,18 +109,26 @@ def dynamic_params(width, height, line_length, out_w, out_h, out_line):
 class Codec:
     """One codec instance driven through the function table, as Codec Engine would."""
 
-    def __init__(self, kind, params=None, device=None):
+    def __init__(self, kind, params=None, device=None, fxns=None):
+        """fxns: optional POINTER(IVIDTRANSCODE_Fxns) of ANOTHER implementation of the same ABI (the
+        boundary tests pass the host-built reference's TRIK_VIDTRANSCODE_CV_FXNS here, so that one
+        driver exercises both sides); default: this library's table for `kind`."""
         if isinstance(kind, str):
             kind = xdm.KIND_OF[kind]
         self.kind = kind
-        self.lib = lib()
-        if device is not None and self.lib.trikb200_setDevice(device) != 0:
-            raise TrikB200Error(last_error())
-        self.fxns = self.lib.trikb200_fxns(kind).contents
+        self.foreign = fxns is not None
         self.InArgs = xdm.in_args_type(kind)
         self.OutArgs = xdm.out_args_type(kind)
-        assert C.sizeof(self.InArgs) == self.lib.trikb200_sizeofInArgs(kind)
-        assert C.sizeof(self.OutArgs) == self.lib.trikb200_sizeofOutArgs(kind)
+        if self.foreign:
+            self.lib = None
+            self.fxns = fxns.contents
+        else:
+            self.lib = lib()
+            if device is not None and self.lib.trikb200_setDevice(device) != 0:
+                raise TrikB200Error(last_error())
+            self.fxns = self.lib.trikb200_fxns(kind).contents
+            assert C.sizeof(self.InArgs) == self.lib.trikb200_sizeofInArgs(kind)
+            assert C.sizeof(self.OutArgs) == self.lib.trikb200_sizeofOutArgs(kind)
         self.params = params if params is not None else default_params(kind)
         # alloc: the CALLER owns the records (vidtranscode_cv_fxns.c:85-102)
         self.memtab = (xdm.IALG_MemRec * 4)()
@@ -171,7 +179,8 @@ class Codec:
         return ret, buf.value.decode()
 
     def set_seed(self, seed):
-        self.lib.trikb200_setSeed(self.handle, int(seed))
+        if not self.foreign:
+            self.lib.trikb200_setSeed(self.handle, int(seed))
 
     # ---- process ---------------------------------------------------------------------------------
     def process_raw(self, in_bufs, out_bufs, in_args, out_args):

@@ -9,6 +9,7 @@ Families
   scene  (F2)  constant background colour, 1-3 filled rectangles / discs of a second colour,
                +-2 LSB luma noise, and a dark vertical band (what a line sensor looks at)
   grid   (F2)  every cell of an MxN grid painted its own colour with ~10 % distractor pixels
+  blobs  (F2)  10-20 saturated red blobs of different sizes + isolated specks on a dark frame
   edge   (F3)  all-zero, all-255, blue-wrap (Y=U=255), grey ramp, metapixel checkerboard, 8 specks
 
 Layouts
@@ -138,6 +139,33 @@ def planes_grid(seed, w, h, m, n):
     return y, u, v
 
 
+def planes_blobs(seed, w, h):
+    """Dark frame with 10-20 separate saturated red blobs of different sizes plus isolated 4x4 specks:
+    what the object sensor ranks (>= 8 labels, distinct and equal sizes)."""
+    p = _randint(seed, 30, 0, 1 << 16, 256)
+    y = np.full((h, w), 24, dtype=np.uint8)
+    u = np.full((h, w // 2), 128, dtype=np.uint8)
+    v = np.full((h, w // 2), 128, dtype=np.uint8)
+    nblobs = 10 + int(p[0] % 11)
+    for k in range(nblobs):
+        q = p[4 + 4 * k: 8 + 4 * k]
+        bh = 4 * (1 + int(q[2]) % max(1, h // 24))
+        bw = 4 * (1 + int(q[3]) % max(1, w // 32))
+        r = 4 * (int(q[0]) % max(1, (h - bh) // 4))
+        c = 4 * (int(q[1]) % max(1, (w - bw) // 4))
+        y[r:r + bh, c:c + bw] = 120
+        u[r:r + bh, c // 2:(c + bw) // 2] = 90
+        v[r:r + bh, c // 2:(c + bw) // 2] = 240
+    for k in range(12):
+        q = p[128 + 2 * k: 130 + 2 * k]
+        r = 4 * (int(q[0]) % (h // 4))
+        c = 4 * (int(q[1]) % (w // 4))
+        y[r:r + 4, c:c + 4] = 120
+        u[r:r + 4, c // 2:c // 2 + 2] = 90
+        v[r:r + 4, c // 2:c // 2 + 2] = 240
+    return y, u, v
+
+
 EDGE_CASES = ("zero", "full", "bluewrap", "greyramp", "checker", "specks", "red", "halves")
 
 
@@ -195,6 +223,8 @@ def make_frame(family, seed, w, h, layout, line_length=None, **kw):
         planes = planes_scene(seed, w, h, band=kw.get("band", True))
     elif family == "grid":
         planes = planes_grid(seed, w, h, kw.get("m", 3), kw.get("n", 3))
+    elif family == "blobs":
+        planes = planes_blobs(seed, w, h)
     else:
         planes = planes_edge(family, w, h)
     return pack(planes[0], planes[1], planes[2], layout, line_length)
