@@ -225,6 +225,11 @@ XDAS_Int32 trikb200_setDevice(XDAS_Int32 device);
 int64_t trikb200_launchCount(void);
 /* tuning knob: CTAs per frame for the sum kernels (0 = heuristic) */
 void trikb200_setSlabsPerFrame(XDAS_Int32 slabs);
+/* tuning knob for A/B measurements of the sum kernels (WO/WL/OL); negative = the measured per-sensor defaults.
+ * v % 100: load path, 0 = register prefetch, 2 or 4 = depth of the per-thread cp.async ring in shared memory;
+ * v / 100: 0 = default kernel per sensor, 1 = first-version kernel, 2 = tuned line kernel (WL/OL).
+ * Unsupported values make the next launch fail with XDM_EFAIL. */
+void trikb200_setLoadStages(XDAS_Int32 stages);
 /* last CUDA / argument error message of this thread ("" if none) */
 const char* trikb200_lastError(void);
 

@@ -1035,6 +1035,7 @@ XDAS_Int32 trikb200_setDevice(XDAS_Int32 device)
 
 int64_t trikb200_launchCount(void) { return launch_count(); }
 void trikb200_setSlabsPerFrame(XDAS_Int32 slabs) { g_slabsPerFrame = slabs; }
+void trikb200_setLoadStages(XDAS_Int32 stages) { set_sum_stages(stages); }
 const char* trikb200_lastError(void) { return t_lastError.c_str(); }
 
 /* test probes: exhaustive pixel functions straight from the device code (tests/test_pixel_gpu.py) */

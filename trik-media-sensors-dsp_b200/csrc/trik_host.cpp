@@ -26,6 +26,10 @@ void v_range_to_keys(uint32_t vf, uint32_t vt, FrameParams& fp)
     klo = (vf == 0u) ? 0u : 0x8000u + vf * 64u;
     const uint32_t khi = (vt == 255u) ? 0xFFFFu : 0x8000u + vt * 64u + 63u;
     n = khi - klo;
+    // keep N + 1 representable in a lane: key 65535 (value 32767) is unreachable -- 129*U + 74*Y = 50439 has
+    // no solution in bytes -- so an all-inclusive range loses nothing by stopping at 65534
+    if (n == 0xFFFFu)
+      n = 0xFFFEu;
   }
   const uint32_t negKlo = (0x10000u - klo) & 0xFFFFu;
   fp.negKlo2 = negKlo * 0x10001u;

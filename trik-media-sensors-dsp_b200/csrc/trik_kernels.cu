@@ -20,6 +20,29 @@
 namespace trikb200 {
 
 static long long g_launches = 0;
+// Tuning state.  Default (-1): the measured best per sensor on B200 --
+//   WL: tuned line kernel, cp.async ring of 4;  OL: first-version kernel, ring of 2;  WO: register prefetch.
+// trikb200_setLoadStages(v): v % 100 = load path (0 register prefetch, 2 / 4 ring depth),
+//   v / 100 = 0 per-sensor default kernel, 1 force the first-version kernel, 2 force the tuned line kernel.
+static int g_tuneStages = -1;
+static int g_tuneKernel = 0;
+static bool g_legacyLineKernel = false;      // resolved per launch
+static int g_sumStages = 0;                  // resolved per launch
+void set_sum_stages(int v)
+{
+  if (v < 0) { g_tuneStages = -1; g_tuneKernel = 0; return; }
+  g_tuneStages = v % 100;
+  g_tuneKernel = v / 100;
+}
+static void resolve_tuning(int kind)
+{
+  const bool tunedDefault = (kind == KIND_WL);
+  g_legacyLineKernel = g_tuneKernel == 1 ? true : (g_tuneKernel == 2 ? false : !tunedDefault);
+  if (g_tuneStages >= 0)
+    g_sumStages = g_tuneStages;
+  else
+    g_sumStages = kind == KIND_WL ? 4 : (kind == KIND_OL ? 2 : 0);
+}
 extern long long g_launches_grid;
 extern long long g_launches_detect;
 long long launch_count() { return g_launches + g_launches_grid + g_launches_detect; }
@@ -106,7 +129,12 @@ __device__ void finalize_sum(const Geometry& g, const FrameParams& p, uint32_t f
 // ---------------------------------------------------------------------------------------------
 // the sum kernel
 // ---------------------------------------------------------------------------------------------
-template <int KIND>
+// STAGES == 0: the next chunk is prefetched into registers (one load in flight per thread).
+// STAGES >= 2: every thread keeps a PRIVATE ring of STAGES chunks in shared memory filled by
+//   cp.async (LDGSTS, L2-only .cg): STAGES-1 loads in flight per thread with no register cost, and
+//   because a thread only ever reads the slots it filled itself, no CTA barrier is needed --
+//   cp.async.wait_group orders the thread's own copies.
+template <int KIND, int STAGES>
 __global__ void __launch_bounds__(1024)
 sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
            const int paramStride, SumAcc* __restrict__ acc, TargetOut* __restrict__ out,
@@ -148,21 +176,62 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
   int row = r0 + rr;
   const uint8_t* ptr = base + (size_t)row * g.lineLength;
   const size_t chromaOfs = (size_t)g.height * g.lineLength;
+  extern __shared__ uint4 s_ring[];          // STAGES x blockDim (x2 planes for YUV422P), thread-private slots
+  constexpr int PLANES = PLANAR ? 2 : 1;
   uint4 cur = make_uint4(0, 0, 0, 0), curC = make_uint4(0, 0, 0, 0);
-  if (row < r1)
+  int fillRow = row;                         // next row to request (STAGES > 0)
+  const uint8_t* fillPtr = ptr;
+  if (STAGES == 0)
   {
-    cur = ld_stream(ptr);
-    if (PLANAR) curC = ld_stream(ptr + chromaOfs);
+    if (row < r1)
+    {
+      cur = ld_stream(ptr);
+      if (PLANAR) curC = ld_stream(ptr + chromaOfs);
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int sIdx = 0; sIdx < (STAGES > 0 ? STAGES - 1 : 0); ++sIdx)
+    {
+      if (fillRow < r1)
+      {
+        cp_async16(&s_ring[(sIdx * PLANES) * blockDim.x + t], fillPtr);
+        if (PLANAR) cp_async16(&s_ring[(sIdx * PLANES + 1) * blockDim.x + t], fillPtr + chromaOfs);
+      }
+      cp_async_commit();
+      fillRow += rpi;
+      fillPtr += rowStep;
+    }
   }
   for (uint32_t it = 0; row < r1; ++it)
   {
-    // prefetch the next row's chunk before working on this one
     uint4 nxt = make_uint4(0, 0, 0, 0), nxtC = make_uint4(0, 0, 0, 0);
     const int nrow = row + rpi;
-    if (nrow < r1)
+    if (STAGES == 0)
     {
-      nxt = ld_stream(ptr + rowStep);
-      if (PLANAR) nxtC = ld_stream(ptr + rowStep + chromaOfs);
+      // prefetch the next row's chunk before working on this one
+      if (nrow < r1)
+      {
+        nxt = ld_stream(ptr + rowStep);
+        if (PLANAR) nxtC = ld_stream(ptr + rowStep + chromaOfs);
+      }
+    }
+    else
+    {
+      const int fillSlot = (int)((it + STAGES - 1) % STAGES);
+      if (fillRow < r1)
+      {
+        cp_async16(&s_ring[(fillSlot * PLANES) * blockDim.x + t], fillPtr);
+        if (PLANAR) cp_async16(&s_ring[(fillSlot * PLANES + 1) * blockDim.x + t], fillPtr + chromaOfs);
+      }
+      cp_async_commit();
+      fillRow += rpi;
+      fillPtr += rowStep;
+      cp_async_wait<STAGES - 1>();
+      const int slot = (int)(it % STAGES);
+      cur = s_ring[(slot * PLANES) * blockDim.x + t];
+      if (PLANAR) curC = s_ring[(slot * PLANES + 1) * blockDim.x + t];
     }
 
     uint32_t Sc = 0;                       // fail lanes of this chunk
@@ -205,7 +274,10 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
       if ((uint32_t)row - p.hStart <= p.hStop - p.hStart && p.hStart <= p.hStop)
         SC += Sc;
 
-    cur = nxt; curC = nxtC;
+    if (STAGES == 0)
+    {
+      cur = nxt; curC = nxtC;
+    }
     row = nrow;
     ptr += rowStep;
   }
@@ -271,9 +343,296 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// the line-sensor kernel (WL, OL): V-only threshold, tuned instruction mix
+// ---------------------------------------------------------------------------------------------
+// ncu on the first version showed the ALU pipe (LOP3/PRMT/VIADD/VIMNMX, half rate) as the busiest
+// unit with the FMA pipe (IMAD/IDP.4A) at half its load.  This version moves everything that can
+// move onto the FMA pipe and trims the bookkeeping:
+//   * the blue chroma term is replicated into both lanes by an IMAD (x 0x10001) instead of a PRMT.
+//   * the fail test leaves {N, N+1} in each lane (pass, fail) instead of {0,1}; lane-isolated
+//     VIADD.16x2 accumulates that per pair position, and the known pass contribution
+//     iterations*N is subtracted modulo 2^16 at the end.  No per-word fix-up instructions.
+//   * OL: the column window is folded into the per-lane cap constant, and the cross band (rows
+//     hStart..hStop, a contiguous run of a thread's iterations) is the difference of two snapshots
+//     of the accumulators -- nothing per pixel.
+// Per two pixels: 7 FMA-pipe + 6 ALU-pipe instructions in both layouts.
+// {N, N+1} lanes (pass, fail) of a pixel pair from its key lanes.
+// IMAD / IDP.4A issue on the FMA pipe and LOP3 / PRMT / VIADD / VIMNMX on the ALU pipe, both at one warp
+// instruction per two cycles per scheduler, so the pair is split 7 : 6 between them:
+//   FMA: 74*yy, three IDP.4A chroma terms, two replicate-and-add IMADs (red, green), one replicate IMAD (blue)
+//   ALU: luma extraction, VIADD.16x2 (blue, wraps like the reference's int16), VIMNMX3, VIADDMNMX, VIMNMX, VIADD.16x2 (count)
+__device__ __forceinline__ uint32_t vtest_lanes(uint32_t yy, uint32_t cw, const ChromaCoef cf,
+                                                uint32_t negKlo2, uint32_t n2, uint32_t cap2)
+{
+  const uint32_t y74 = yy * 74u;
+  const uint32_t cr = dp4a_uu(cw, cf.r, KEY_BIAS - 14248u);
+  const uint32_t cg = (uint32_t)dp4a_us(cw, cf.g, (int32_t)(KEY_BIAS + 8696u));
+  const uint32_t cb = dp4a_uu(cw, cf.b, KEY_BIAS - 17672u);
+  const uint32_t kr = cr * 0x10001u + y74;
+  const uint32_t kg = cg * 0x10001u + y74;
+  const uint32_t kb = __vadd2(cb * 0x10001u, y74);
+  const uint32_t km = __vimax3_u16x2(kr, kg, kb);
+  return __vminu2(__vmaxu2(__vadd2(km, negKlo2), n2), cap2);
+}
+
+// YUYV: measured slightly faster with the luma term folded into the dot product -- one IDP.4A per pixel
+// and channel yields the finished 32-bit key (74*Y + 102*V + c, ...), two keys are packed into lanes by
+// one IMAD (red, green: cannot overflow a lane) or one PRMT (blue: truncation to 16 bits IS the wrap).
+// 8 FMA-pipe + 5 ALU-pipe instructions per pair.
+__device__ __forceinline__ uint32_t vtest_yuyv(uint32_t w, uint32_t negKlo2, uint32_t n2, uint32_t cap2)
+{
+  const uint32_t r0 = dp4a_uu(w, 0x6600004Au, KEY_BIAS - 14248u);                       // 74*Y0 + 102*V + c
+  const uint32_t r1 = dp4a_uu(w, 0x664A0000u, KEY_BIAS - 14248u);                       // 74*Y1 + 102*V + c
+  const uint32_t g0 = (uint32_t)dp4a_us(w, 0xCC00E74Au, (int32_t)(KEY_BIAS + 8696u));   // 74*Y0 - 25*U - 52*V + c
+  const uint32_t g1 = (uint32_t)dp4a_us(w, 0xCC4AE700u, (int32_t)(KEY_BIAS + 8696u));
+  const uint32_t b0 = dp4a_uu(w, 0x0000814Au, KEY_BIAS - 17672u);                       // 74*Y0 + 129*U + c (may exceed 16 bits)
+  const uint32_t b1 = dp4a_uu(w, 0x004A8100u, KEY_BIAS - 17672u);
+  const uint32_t kr = r1 * 65536u + r0;
+  const uint32_t kg = g1 * 65536u + g0;
+  const uint32_t kb = __byte_perm(b0, b1, 0x5410);
+  const uint32_t km = __vimax3_u16x2(kr, kg, kb);
+  return __vminu2(__vmaxu2(__vadd2(km, negKlo2), n2), cap2);
+}
+
+// pair J (0/1) of a luma word L and the chroma word Cw under it
+template <int J>
+__device__ __forceinline__ uint32_t vtest_planar(uint32_t L, uint32_t Cw, uint32_t negKlo2, uint32_t n2, uint32_t cap2)
+{
+  return vtest_lanes(__byte_perm(L, 0u, J ? 0x4342 : 0x4140), Cw, J ? coef_planar1() : coef_planar0(), negKlo2, n2, cap2);
+}
+
+__device__ __forceinline__ uint32_t lanes_sub(uint32_t a, uint32_t b)      // lane-wise (a - b) mod 2^16
+{
+  return __vadd2(a, __vadd2(~b, 0x00010001u));
+}
+__device__ __forceinline__ uint32_t lanes_total(uint32_t a) { return (a & 0xFFFFu) + (a >> 16); }
+
+__device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ uint2 ld_stream8(const void* p)
+{
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// A thread owns 8 pixels of a row in BOTH layouts: one 16-byte YUYV chunk, or 8 luma bytes + the 8
+// chroma bytes under them (YUV422P); either way the chunk is four 32-bit "pair" slots in one uint4
+// (YUV422P: x,y = luma words, z,w = chroma words), so the cp.async ring is identical.
+// MAXT = 512 asks ptxas for three resident CTAs of up to 512 threads (<= 40 registers per thread), which
+// is what the usual 256..512-thread configurations want; MAXT = 1024 is the catch-all for very wide rows.
+template <bool PLANAR, int STAGES, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 512 ? 3 : 1)
+vsum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+            const int paramStride, SumAcc* __restrict__ acc, TargetOut* __restrict__ out,
+            const int slabs, const int rowsPerSlab, const int cpr, const int rpi)
+{
+  __shared__ uint32_t s_red[32][4];
+  extern __shared__ uint4 s_ring[];
+
+  const int frame = blockIdx.x / slabs;
+  const int slab  = blockIdx.x - frame * slabs;
+  const int t  = threadIdx.x;
+  const int cc = t % cpr;
+  const int rr = t / cpr;
+  const FrameParams p = params[(size_t)frame * paramStride];
+
+  const int r0 = slab * rowsPerSlab;
+  const int r1 = min(r0 + rowsPerSlab, g.height);
+  const int firstRow = r0 + rr;
+  const int iters = firstRow < r1 ? (r1 - firstRow + rpi - 1) / rpi : 0;
+  const uint8_t* ptr = frames + (size_t)frame * g.frameStride + (size_t)cc * (PLANAR ? 8u : 16u)
+                     + (size_t)firstRow * g.lineLength;
+  const size_t rowStep = (size_t)rpi * g.lineLength;
+  const size_t chromaOfs = (size_t)g.height * g.lineLength;
+
+  const uint32_t negKlo2 = p.negKlo2, n2 = p.n2;
+  const uint32_t nLane = n2 & 0xFFFFu;
+  const uint32_t np1 = n2 + 0x00010001u;               // N + 1 in both lanes (N <= 65534 by construction)
+  // per-position cap: N+1 where the pixel counts, N (== "always pass") where OL's column window
+  // (columns 5..W-5) excludes it: chunk 0 loses its pixels 0..4, the last chunk its pixels 4..7
+  uint32_t cap01 = np1, cap2 = np1, cap3 = np1;
+  if (PLANAR)
+  {
+    if (cc == 0)       { cap01 = n2; cap2 = (np1 & 0xFFFF0000u) | nLane; }
+    if (cc == cpr - 1) { cap2 = n2; cap3 = n2; }
+  }
+
+  // OL cross band as a run of this thread's iterations [itA, itB)
+  int itA = 0, itB = 0;
+  if (PLANAR && p.hStart <= p.hStop)
+  {
+    const long long a = (long long)p.hStart - firstRow, b = (long long)p.hStop + 1 - firstRow;
+    itA = a <= 0 ? 0 : (int)min((long long)iters, (a + rpi - 1) / rpi);
+    itB = b <= 0 ? 0 : (int)min((long long)iters, (b + rpi - 1) / rpi);
+  }
+
+  uint32_t S0 = 0u, S1 = 0u, S2 = 0u, S3 = 0u;
+  uint32_t snapA = 0u, snapB = 0u;
+
+  const uint8_t* fillPtr = ptr;
+  int fillIt = 0;
+  uint4 cur = make_uint4(0, 0, 0, 0);
+  auto request = [&](uint4* slot, const uint8_t* src)
+  {
+    if (PLANAR)
+    {
+      cp_async8(slot, src);
+      cp_async8(reinterpret_cast<uint8_t*>(slot) + 8, src + chromaOfs);
+    }
+    else
+      cp_async16(slot, src);
+  };
+  auto load_now = [&](const uint8_t* src) -> uint4
+  {
+    if (PLANAR)
+    {
+      const uint2 l = ld_stream8(src), c = ld_stream8(src + chromaOfs);
+      return make_uint4(l.x, l.y, c.x, c.y);
+    }
+    return ld_stream(src);
+  };
+  if (STAGES == 0)
+  {
+    if (iters > 0)
+      cur = load_now(ptr);
+  }
+  else
+  {
+#pragma unroll
+    for (int sIdx = 0; sIdx < (STAGES > 0 ? STAGES - 1 : 0); ++sIdx)
+    {
+      if (fillIt < iters)
+        request(&s_ring[sIdx * blockDim.x + t], fillPtr);
+      cp_async_commit();
+      ++fillIt;
+      fillPtr += rowStep;
+    }
+  }
+
+  for (int it = 0; it < iters; ++it)
+  {
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (STAGES == 0)
+    {
+      if (it + 1 < iters)
+        nxt = load_now(ptr + rowStep);
+      ptr += rowStep;
+    }
+    else
+    {
+      if (fillIt < iters)
+        request(&s_ring[((it + STAGES - 1) % STAGES) * blockDim.x + t], fillPtr);
+      cp_async_commit();
+      ++fillIt;
+      fillPtr += rowStep;
+      cp_async_wait<STAGES - 1>();
+      cur = s_ring[(it % STAGES) * blockDim.x + t];
+    }
+
+    if (PLANAR)
+    {
+      if (it == itA || it == itB)
+      {
+        const uint32_t tot = __vadd2(__vadd2(S0, S1), __vadd2(S2, S3));
+        if (it == itA) snapA = tot;
+        if (it == itB) snapB = tot;
+      }
+      S0 = __vadd2(S0, vtest_planar<0>(cur.x, cur.z, negKlo2, n2, cap01));
+      S1 = __vadd2(S1, vtest_planar<1>(cur.x, cur.z, negKlo2, n2, cap01));
+      S2 = __vadd2(S2, vtest_planar<0>(cur.y, cur.w, negKlo2, n2, cap2));
+      S3 = __vadd2(S3, vtest_planar<1>(cur.y, cur.w, negKlo2, n2, cap3));
+    }
+    else
+    {
+      S0 = __vadd2(S0, vtest_yuyv(cur.x, negKlo2, n2, np1));
+      S1 = __vadd2(S1, vtest_yuyv(cur.y, negKlo2, n2, np1));
+      S2 = __vadd2(S2, vtest_yuyv(cur.z, negKlo2, n2, np1));
+      S3 = __vadd2(S3, vtest_yuyv(cur.w, negKlo2, n2, np1));
+    }
+    if (STAGES == 0)
+      cur = nxt;
+  }
+
+  // every lane holds (iterations * N + fails) mod 2^16; fails <= iterations <= 128 per lane
+  const uint32_t total = __vadd2(__vadd2(S0, S1), __vadd2(S2, S3));
+  if (PLANAR)
+  {
+    if (itA >= iters) snapA = total;
+    if (itB >= iters) snapB = total;
+  }
+  const uint32_t passBias2 = (((uint32_t)iters * nLane) & 0xFFFFu) * 0x10001u;
+  const uint32_t f0 = lanes_sub(S0, passBias2), f1 = lanes_sub(S1, passBias2);
+  const uint32_t f2 = lanes_sub(S2, passBias2), f3 = lanes_sub(S3, passBias2);
+  uint32_t fails = lanes_total(f0) + lanes_total(f1) + lanes_total(f2) + lanes_total(f3);
+  // in-chunk pixel index of pair k, lane e is 2k + e
+  const uint32_t inIdx = 2u * (lanes_total(f1) + 2u * lanes_total(f2) + 3u * lanes_total(f3))
+                       + (f0 >> 16) + (f1 >> 16) + (f2 >> 16) + (f3 >> 16);
+  uint32_t sxFail = fails * ((uint32_t)cc * 8u) + inIdx;
+  uint32_t crossFail = 0u;
+  if (PLANAR)
+  {
+    const uint32_t bandBias2 = (((uint32_t)(itB - itA) * 4u * nLane) & 0xFFFFu) * 0x10001u;
+    crossFail = lanes_total(lanes_sub(lanes_sub(snapB, snapA), bandBias2));
+  }
+
+  __syncthreads();
+  const unsigned am = __activemask();
+  fails  = __reduce_add_sync(am, fails);
+  sxFail = __reduce_add_sync(am, sxFail);
+  if (PLANAR) crossFail = __reduce_add_sync(am, crossFail);
+  const int warp = t >> 5, lane = t & 31, nwarps = (blockDim.x + 31) >> 5;
+  if (lane == 0)
+  {
+    s_red[warp][0] = fails; s_red[warp][1] = sxFail; s_red[warp][3] = crossFail;
+  }
+  __syncthreads();
+  if (warp == 0)
+  {
+    uint32_t a = 0, b = 0, d = 0;
+    if (lane < nwarps) { a = s_red[lane][0]; b = s_red[lane][1]; d = s_red[lane][3]; }
+    const unsigned fm = __activemask();
+    a = __reduce_add_sync(fm, a);
+    b = __reduce_add_sync(fm, b);
+    if (PLANAR) d = __reduce_add_sync(fm, d);
+    if (lane == 0)
+    {
+      SumAcc* fa = acc + frame;
+      bool last = true;
+      if (slabs > 1)
+      {
+        atomicAdd(&fa->fails, a);
+        atomicAdd(&fa->sxFail, b);
+        if (PLANAR) atomicAdd(&fa->crossFail, d);
+        __threadfence();
+        last = (atomicAdd(&fa->done, 1u) == (uint32_t)slabs - 1u);
+        if (last)
+        {
+          __threadfence();
+          a = atomicExch(&fa->fails, 0u);
+          b = atomicExch(&fa->sxFail, 0u);
+          d = atomicExch(&fa->crossFail, 0u);
+          atomicExch(&fa->done, 0u);
+        }
+      }
+      if (last)
+      {
+        if (PLANAR) finalize_sum<KIND_OL>(g, p, a, b, 0u, d, out + frame);
+        else        finalize_sum<KIND_WL>(g, p, a, b, 0u, 0u, out + frame);
+      }
+    }
+  }
+}
+
+static int sum_chunk_pixels(int kind) { return (kind == KIND_OL && g_legacyLineKernel) ? 16 : 8; }
+
 int sum_sensor_block_threads(int kind, int width)
 {
-  const int cpr = width / (kind == KIND_OL ? 16 : 8);
+  const int cpr = width / sum_chunk_pixels(kind);
   if (cpr <= 0 || cpr > 1024)
     return 0;
   int k = (256 + cpr - 1) / cpr;
@@ -294,10 +653,11 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
 {
   if (numFrames <= 0)
     return cudaSuccess;
+  resolve_tuning(kind);
   const int threads = sum_sensor_block_threads(kind, g.width);
   if (threads <= 0)
     return cudaErrorInvalidValue;
-  const int cpr = g.width / (kind == KIND_OL ? 16 : 8);
+  const int cpr = g.width / sum_chunk_pixels(kind);
   const int rpi = threads / cpr;
   // SI lanes (WO) hold sum(it * fails_per_chunk) <= 8 * I*(I-1)/2: keep I <= 128 iterations per slab
   const int maxRowsPerSlab = 128 * rpi;
@@ -319,20 +679,57 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
   const long long grid = (long long)numFrames * slabs;
   if (grid > 0x7FFFFFFFLL)
     return cudaErrorInvalidValue;
+  const int stages = g_sumStages;
+  const size_t ringBytes = (size_t)stages * threads * sizeof(uint4) * ((kind == KIND_OL && g_legacyLineKernel) ? 2 : 1);
+#define TRIK_LAUNCH_SUM(K, ST)                                                                                   \
+  do {                                                                                                           \
+    if (ringBytes > 48 * 1024)                                                                                   \
+      cudaFuncSetAttribute(sum_kernel<K, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);      \
+    sum_kernel<K, ST><<<(unsigned)grid, threads, ringBytes, stream>>>(g, frames, params, paramStride, acc, out,  \
+                                                                      slabs, rowsPerSlab, cpr, rpi);             \
+  } while (0)
+#define TRIK_LAUNCH_SUM_KIND(K)                                 \
+  switch (stages)                                               \
+  {                                                             \
+    case 0: TRIK_LAUNCH_SUM(K, 0); break;                       \
+    case 2: TRIK_LAUNCH_SUM(K, 2); break;                       \
+    case 4: TRIK_LAUNCH_SUM(K, 4); break;                       \
+    default: return cudaErrorInvalidValue;                      \
+  }
+#define TRIK_LAUNCH_V2(PL, ST, MT)                                                                               \
+  do {                                                                                                           \
+    if (ringBytes > 48 * 1024)                                                                                   \
+      cudaFuncSetAttribute(vsum_kernel<PL, ST, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);\
+    vsum_kernel<PL, ST, MT><<<(unsigned)grid, threads, ringBytes, stream>>>(g, frames, params, paramStride, acc, \
+                                                                            out, slabs, rowsPerSlab, cpr, rpi);  \
+  } while (0)
+#define TRIK_LAUNCH_V(PL, ST)                                   \
+  do { if (threads <= 512) TRIK_LAUNCH_V2(PL, ST, 512); else TRIK_LAUNCH_V2(PL, ST, 1024); } while (0)
+#define TRIK_LAUNCH_V_KIND(PL)                                  \
+  switch (stages)                                               \
+  {                                                             \
+    case 0: TRIK_LAUNCH_V(PL, 0); break;                        \
+    case 2: TRIK_LAUNCH_V(PL, 2); break;                        \
+    case 4: TRIK_LAUNCH_V(PL, 4); break;                        \
+    default: return cudaErrorInvalidValue;                      \
+  }
   switch (kind)
   {
     case KIND_WL:
-      sum_kernel<KIND_WL><<<(unsigned)grid, threads, 0, stream>>>(g, frames, params, paramStride, acc, out, slabs, rowsPerSlab, cpr, rpi);
+      if (g_legacyLineKernel) { TRIK_LAUNCH_SUM_KIND(KIND_WL); } else { TRIK_LAUNCH_V_KIND(false); }
       break;
     case KIND_OL:
-      sum_kernel<KIND_OL><<<(unsigned)grid, threads, 0, stream>>>(g, frames, params, paramStride, acc, out, slabs, rowsPerSlab, cpr, rpi);
+      if (g_legacyLineKernel) { TRIK_LAUNCH_SUM_KIND(KIND_OL); } else { TRIK_LAUNCH_V_KIND(true); }
       break;
-    case KIND_WO:
-      sum_kernel<KIND_WO><<<(unsigned)grid, threads, 0, stream>>>(g, frames, params, paramStride, acc, out, slabs, rowsPerSlab, cpr, rpi);
-      break;
+    case KIND_WO: TRIK_LAUNCH_SUM_KIND(KIND_WO); break;
     default:
       return cudaErrorInvalidValue;
   }
+#undef TRIK_LAUNCH_V_KIND
+#undef TRIK_LAUNCH_V
+#undef TRIK_LAUNCH_V2
+#undef TRIK_LAUNCH_SUM_KIND
+#undef TRIK_LAUNCH_SUM
   ++g_launches;
   return cudaGetLastError();
 }

@@ -82,6 +82,7 @@ cudaError_t launch_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, 
 cudaError_t launch_probe_rgb2hsv(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
 
 int sum_sensor_block_threads(int kind, int width);
+void set_sum_stages(int stages);
 long long launch_count();
 
 } // namespace trikb200

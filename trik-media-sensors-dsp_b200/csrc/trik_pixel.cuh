@@ -137,4 +137,14 @@ __device__ __forceinline__ uint4 ld_stream(const void* p)
   return r;
 }
 
+// ---- cp.async (LDGSTS): 16 bytes global -> shared, L2 only, no register staging ---------------
+__device__ __forceinline__ void cp_async16(void* smemDst, const void* gmemSrc)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 } // namespace trikb200
