@@ -68,9 +68,8 @@ __device__ __forceinline__ uint32_t hsvfail_pair(uint32_t yy, uint32_t cw, const
                                                  const uint16_t* lut43, const uint16_t* lut255,
                                                  uint32_t from, uint32_t to, uint32_t expected)
 {
-  uint32_t h0, h1;
-  hsv_pair(yy, cw, coef, lut43, lut255, h0, h1);
-  return (detect_hsv(h0, from, to, expected) ? 0u : 1u) | (detect_hsv(h1, from, to, expected) ? 0u : 0x10000u);
+  const uint32_t det = detect_pair_bits(yy, cw, coef, lut43, lut255, from, to, expected);
+  return ((det & 1u) ^ 1u) | (((det >> 1) ^ 1u) << 16);
 }
 
 // ---------------------------------------------------------------------------------------------

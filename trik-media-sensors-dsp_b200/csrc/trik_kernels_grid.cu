@@ -228,11 +228,9 @@ oo_bitmap_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fra
       for (int k = 0; k < 8; ++k)
       {
         const uint32_t yy = __byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140);
-        uint32_t h0, h1;
-        hsv_pair(yy, Cw[k >> 1], (k & 1) ? coef_planar1() : coef_planar0(), s_lut43, s_lut255, h0, h1);
-        const uint32_t d0 = detect_hsv(h0, p.from, p.to, p.expected) ? 1u : 0u;
-        const uint32_t d1 = detect_hsv(h1, p.from, p.to, p.expected) ? 1u : 0u;
-        meta[k >> 1] |= (d0 | (d1 << 1)) << (r * 4 + (k & 1) * 2);
+        const uint32_t det = detect_pair_bits(yy, Cw[k >> 1], (k & 1) ? coef_planar1() : coef_planar0(),
+                                              s_lut43, s_lut255, p.from, p.to, p.expected);
+        meta[k >> 1] |= det << (r * 4 + (k & 1) * 2);
       }
     }
     uint2 v;
@@ -402,69 +400,107 @@ struct ObjOut {                                           // == TRIKB200_ObjOutA
 };
 static_assert(sizeof(ObjOut) == 36, "ObjOutArgsAlg layout");
 
+// One warp per frame.  The 32 lanes test 32 metapixels at a time (popcount > 2) and vote; lane 0 then
+// walks only the set bits in raster order and replays the reference's labelling on them.  The label
+// tables live in shared memory when they fit (tablesInSmem), else in the global scratch.
 __global__ void __launch_bounds__(32)
 oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoCluster* __restrict__ clustersAll,
-                  uint16_t* __restrict__ equalAll, const int maxLabels, ObjOut* __restrict__ out, int* __restrict__ labelCounts)
+                  uint16_t* __restrict__ equalAll, const int maxLabels, const int tablesInSmem,
+                  ObjOut* __restrict__ out, int* __restrict__ labelCounts)
 {
-  extern __shared__ uint16_t s_rows[];                    // two label rows of bw entries
+  extern __shared__ __align__(16) uint8_t s_raw[];
   const int frame = blockIdx.x;
+  const int lane = threadIdx.x;
   const int bw = g.width / 4, bh = g.height / 4;
   const uint16_t* bm = bitmaps + (size_t)frame * bw * bh;
-  OoCluster* cl = clustersAll + (size_t)frame * maxLabels;
-  uint16_t* eq = equalAll + (size_t)frame * maxLabels;
-  uint16_t* prev = s_rows;
-  uint16_t* cur = s_rows + bw;
-  for (int i = threadIdx.x; i < 2 * bw; i += 32)
-    s_rows[i] = 0;
+  // shared layout: [clusters (12 B each)] [equal (2 B each)] [two label rows of bw+? u16]
+  OoCluster* cl;
+  uint16_t* eq;
+  uint16_t* rows;
+  if (tablesInSmem)
+  {
+    cl = reinterpret_cast<OoCluster*>(s_raw);
+    eq = reinterpret_cast<uint16_t*>(s_raw + (size_t)maxLabels * sizeof(OoCluster));
+    rows = eq + ((maxLabels + 7) & ~7);
+  }
+  else
+  {
+    cl = clustersAll + (size_t)frame * maxLabels;
+    eq = equalAll + (size_t)frame * maxLabels;
+    rows = reinterpret_cast<uint16_t*>(s_raw);
+  }
+  uint16_t* prev = rows;
+  uint16_t* cur = rows + bw;
+  for (int i = lane; i < 2 * bw; i += 32)
+    rows[i] = 0;
+  int ncl = 1;                                            // label 0 = background (:181-186); lane 0's copy is the truth
+  if (lane == 0)
+  {
+    eq[0] = 0;
+    cl[0] = OoCluster{0, 0, 0};
+  }
   __syncwarp();
-  if (threadIdx.x != 0)
-    return;
 
-  int ncl = 1;                                            // label 0 = background (:181-186)
-  eq[0] = 0;
-  cl[0] = OoCluster{0, 0, 0};
   for (int row = 0; row < bh; ++row)
   {
-    for (int col = 0; col < bw; ++col)
+    for (int base = 0; base < bw; base += 32)
     {
-      uint16_t lab = 0;
-      if (__popc((unsigned)bm[row * bw + col]) > 2)       // pop(...) > METAPIX_SIZE/2 (:192)
+      const int col = base + lane;
+      bool on = false;
+      if (col < bw)
       {
-        uint16_t a[4] = {0, 0, 0, 0};                     // left, up-left, up, up-right (:69-83)
-        if (row != 0)
+        on = __popc((unsigned)bm[row * bw + col]) > 2;    // pop(...) > METAPIX_SIZE/2 (:192)
+        cur[col] = 0;
+      }
+      unsigned mask = __ballot_sync(0xFFFFFFFFu, on);
+      __syncwarp();
+      if (lane == 0)
+      {
+        while (mask)
         {
-          a[2] = prev[col];
-          if (col != 0) a[1] = prev[col - 1];
-          if (col != bw - 1) a[3] = prev[col + 1];
-        }
-        if (col != 0) a[0] = cur[col - 1];
-        uint16_t v = a[0];                                // min(): smallest non-zero (:44-52)
+          const int c = base + __ffs((int)mask) - 1;
+          mask &= mask - 1;
+          uint16_t a[4] = {0, 0, 0, 0};                   // left, up-left, up, up-right (:69-83)
+          if (row != 0)
+          {
+            a[2] = prev[c];
+            if (c != 0) a[1] = prev[c - 1];
+            if (c != bw - 1) a[3] = prev[c + 1];
+          }
+          if (c != 0) a[0] = cur[c - 1];
+          uint16_t v = a[0];                              // min(): smallest non-zero (:44-52)
 #pragma unroll
-        for (int n = 1; n < 4; ++n)
-          if ((a[n] < v && a[n] != 0) || v == 0)
-            v = a[n];
-        if (v)
-        {
-          lab = v;
-          cl[v].x += col; cl[v].y += row; cl[v].size += 1;
+          for (int n = 1; n < 4; ++n)
+            if ((a[n] < v && a[n] != 0) || v == 0)
+              v = a[n];
+          uint16_t lab = 0;
+          if (v)
+          {
+            lab = v;
+            cl[v].x += c; cl[v].y += row; cl[v].size += 1;
 #pragma unroll
-          for (int n = 0; n < 4; ++n)
-            if (a[n])
-              if (!(a[n] == v || eq[a[n]] == eq[v]))
-                eq[a[n]] = eq[v];
-        }
-        else if (ncl < maxLabels)
-        {
-          lab = (uint16_t)ncl;                            // a new label starts with ZERO mass (:104-111)
-          eq[ncl] = (uint16_t)ncl;
-          cl[ncl] = OoCluster{0, 0, 0};
-          ++ncl;
+            for (int n = 0; n < 4; ++n)
+              if (a[n])
+                if (!(a[n] == v || eq[a[n]] == eq[v]))
+                  eq[a[n]] = eq[v];
+          }
+          else if (ncl < maxLabels)
+          {
+            lab = (uint16_t)ncl;                          // a new label starts with ZERO mass (:104-111)
+            eq[ncl] = (uint16_t)ncl;
+            cl[ncl] = OoCluster{0, 0, 0};
+            ++ncl;
+          }
+          cur[c] = lab;
         }
       }
-      cur[col] = lab;
+      __syncwarp();
     }
     uint16_t* tmp = prev; prev = cur; cur = tmp;
   }
+  if (lane != 0)
+    return;
+
   for (int i = 0; i < ncl; ++i)                           // postProcessing (:115-124)
   {
     const int e = eq[i];
@@ -530,9 +566,14 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
-  const size_t smem = (size_t)2 * (g.width / 4) * sizeof(uint16_t);
+  const size_t rowBytes = (size_t)2 * (g.width / 4) * sizeof(uint16_t);
+  const size_t tableBytes = (size_t)maxLabels * sizeof(OoCluster) + (size_t)((maxLabels + 7) & ~7) * sizeof(uint16_t);
+  const int tablesInSmem = (tableBytes + rowBytes <= 200 * 1024) ? 1 : 0;
+  const size_t smem = rowBytes + (tablesInSmem ? tableBytes : 0);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(oo_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   oo_cluster_kernel<<<(unsigned)numFrames, 32, smem, stream>>>(g, bitmaps, reinterpret_cast<OoCluster*>(clusters), equal,
-                                                               maxLabels, reinterpret_cast<ObjOut*>(out), labelCounts);
+                                                               maxLabels, tablesInSmem, reinterpret_cast<ObjOut*>(out), labelCounts);
   ++g_launches_grid;
   return cudaGetLastError();
 }

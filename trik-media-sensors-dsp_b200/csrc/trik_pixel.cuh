@@ -128,6 +128,58 @@ __device__ __forceinline__ void hsv_pair(uint32_t yy, uint32_t cw, const ChromaC
   hsv1 = hsv_from_rgb8((int32_t)(r2 >> 16), (int32_t)(g2 >> 16), (int32_t)(b2 >> 16), lut43, lut255);
 }
 
+// ---- threshold of a pixel pair with warp-level early out --------------------------------------
+// det = ((hsv <u4 from) | (hsv >u4 to)) == expected with expected in {0,1}: S and V must always be inside
+// their bounds, only the hue test can be inverted.  So V (a max3 on the keys) and S (one LUT fetch per
+// pixel) are tested first, and the expensive hue (three channel clamps, sector select, second LUT) is
+// only computed when some lane of the warp still has a candidate -- on frames where the wanted colour is
+// a small part of the picture most warps stop after the cheap tests.  Bit 0 / bit 1 = pixel 0 / 1.
+__device__ __forceinline__ uint32_t detect_pair_bits(uint32_t yy, uint32_t cw, const ChromaCoef coef,
+                                                     const uint16_t* __restrict__ lut43,
+                                                     const uint16_t* __restrict__ lut255,
+                                                     uint32_t from, uint32_t to, uint32_t expected)
+{
+  uint32_t kr, kg, kb;
+  rgb_keys(yy, cw, coef, kr, kg, kb);
+  const uint32_t mx2 = chan8_from_key(__vimax3_u16x2(kr, kg, kb));     // V of both pixels, 0x00VV00VV
+  const uint32_t vf = (from >> 16) & 0xFFu, vt = (to >> 16) & 0xFFu;
+  // 8-bit values in 16-bit lanes leave room for a guard bit: bit 15 of (x + 0x8000 - lo) <=> x >= lo
+  const uint32_t vIn = (mx2 + (0x8000u - vf) * 0x10001u) & ~(mx2 + (0x7FFFu - vt) * 0x10001u) & 0x80008000u;
+  const unsigned am = __activemask();
+  if (!__any_sync(am, vIn != 0u))
+    return 0u;
+  const uint32_t mn2 = chan8_from_key(__vimin3_u16x2(kr, kg, kb));
+  const uint32_t d2 = mx2 - mn2;                                       // lanes >= 0, no borrow
+  const uint32_t sf = (from >> 8) & 0xFFu, st = (to >> 8) & 0xFFu;
+  const uint32_t s0 = (((uint32_t)lut255[mx2 & 0xFFFFu] * (d2 & 0xFFFFu)) >> 8) & 0xFFu;
+  const uint32_t s1 = (((uint32_t)lut255[mx2 >> 16] * (d2 >> 16)) >> 8) & 0xFFu;
+  uint32_t cand = 0u;
+  if ((vIn & 0x8000u) && s0 >= sf && s0 <= st) cand |= 1u;
+  if ((vIn & 0x80000000u) && s1 >= sf && s1 <= st) cand |= 2u;
+  if (!__any_sync(am, cand != 0u))
+    return 0u;
+  // hue: (off + lut43[d] * diff) >> 8 & 255 with the sector chosen as the reference's _cmpeq2 does
+  const uint32_t r2 = chan8_from_key(kr), g2 = chan8_from_key(kg), b2 = chan8_from_key(kb);
+  const uint32_t hf = from & 0xFFu, ht = to & 0xFFu;
+  uint32_t det = 0u;
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+  {
+    const int32_t r = (int32_t)(e ? r2 >> 16 : r2 & 0xFFFFu), g = (int32_t)(e ? g2 >> 16 : g2 & 0xFFFFu);
+    const int32_t b = (int32_t)(e ? b2 >> 16 : b2 & 0xFFFFu);
+    const int32_t mx = (int32_t)(e ? mx2 >> 16 : mx2 & 0xFFFFu), d = (int32_t)(e ? d2 >> 16 : d2 & 0xFFFFu);
+    int32_t off, diff;
+    if (mx == g)      { off = 21845; diff = b - r; }
+    else if (mx == b) { off = 43690; diff = r - g; }
+    else              { off = 0;     diff = g - b; }
+    const uint32_t h = (((uint32_t)(off + (int32_t)lut43[d] * diff)) >> 8) & 0xFFu;
+    const uint32_t hout = (h < hf || h > ht) ? 1u : 0u;
+    if ((cand >> e) & 1u)
+      det |= (hout == expected ? 1u : 0u) << e;
+  }
+  return det;
+}
+
 // ---- 128-bit streaming load ------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld_stream(const void* p)
 {
