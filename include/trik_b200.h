@@ -202,12 +202,31 @@ typedef struct TRIKB200_Batch {
     const int64_t* seeds;      /* per-frame srand() seed for the annealed auto-detect, NULL = time(NULL) as the reference */
     void*       stream;        /* cudaStream_t, NULL = the handle's stream */
     XDAS_Int32  flags;         /* TRIKB200_BATCH_* */
+    const XDAS_Int32* streamIds; /* optional: frame i belongs to logical stream streamIds[i] in [0, numStreams).  Every
+                                  stream has its own carried state inside the handle (as if it were its own codec
+                                  instance of this geometry), frames of one stream are taken in batch order; one launch
+                                  serves all streams.  NULL = one stream, the handle itself.  Stream states are reset
+                                  by control(XDM_SETPARAMS) like the handle's own. */
+    XDAS_Int32  numStreams;
 } TRIKB200_Batch;
 
 /* n frames through one handle == n sequential process() calls (without the preview image).
  * Returns IVIDTRANSCODE_EOK, or IVIDTRANSCODE_EFAIL (bad pointers / sizes / CUDA error) with
  * nothing written to outArgsAlg. */
 XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Batch* batch);
+
+/* Mixed sensors in one call (BASELINE.json config 4: line + object + mxn instances over many streams):
+ * a table of {handle, frame} pairs with HOST frames.  Entries of one handle are processed in table order
+ * (== sequential process() calls on that handle); different handles run concurrently on their own CUDA
+ * streams.  seed: srand() seed for an annealed auto-detect (negative = time(NULL)). */
+typedef struct TRIKB200_MixedEntry {
+    IVIDTRANSCODE_Handle handle;
+    const void*          frame;       /* host pointer to one frame of the handle's geometry */
+    const void*          inArgsAlg;   /* InArgsAlg of the handle's kind */
+    void*                outArgsAlg;  /* OutArgsAlg of the handle's kind */
+    int64_t              seed;
+} TRIKB200_MixedEntry;
+XDAS_Int32 trikb200_processMixed(const TRIKB200_MixedEntry* entries, XDAS_Int32 numEntries);
 
 /* wait for everything enqueued on the handle (TRIKB200_BATCH_ASYNC) */
 XDAS_Int32 trikb200_synchronize(IVIDTRANSCODE_Handle handle);
@@ -230,6 +249,8 @@ void trikb200_setSlabsPerFrame(XDAS_Int32 slabs);
  * v / 100: 0 = default kernel per sensor, 1 = first-version kernel, 2 = tuned line kernel (WL/OL).
  * Unsupported values make the next launch fail with XDM_EFAIL. */
 void trikb200_setLoadStages(XDAS_Int32 stages);
+/* tuning knob: target CTA size of the sum kernels (rounded to a whole number of rows per iteration), 0 = default */
+void trikb200_setBlockThreads(XDAS_Int32 threads);
 /* last CUDA / argument error message of this thread ("" if none) */
 const char* trikb200_lastError(void);
 

@@ -248,3 +248,84 @@ def test_annealed_autodetect_matches_oracle(kind, size):
     r, oa = codec.process(frames[2], ia, seed=seeds[2])
     assert r == 0 and detect_fields(oa.alg) == detect_fields(outs[2])
     codec.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# mixed sensor instances in one call (BASELINE config 4)
+# ---------------------------------------------------------------------------------------------
+def test_mixed_streams_equal_sequential_process():
+    from trik_media_sensors_dsp_b200 import process_mixed
+    w, h = 320, 240
+    kinds = ["wo", "wl", "ol", "oo", "om"]
+    streams = []
+    for si in range(15):                                  # 15 streams, kinds cycling, 4 frames each
+        kind = kinds[si % 5]
+        streams.append((kind, open_sensor(kind, w, h), oracle.OracleSensor(kind, w, h)))
+
+    def args_for(kind, t):
+        if kind == "oo":
+            a = (1, 0, 20, 80, 20, 50, 30, 0) if t == 0 else (0, 0, 0, 0, 0, 0, 0, 0)    # range persists
+            return xdm.ObjInArgsAlg(*a), oracle.ObjInArgs(*a)
+        if kind == "om":
+            return xdm.MxnInArgsAlg(3 + t % 3, 4), oracle.MxnInArgs(3 + t % 3, 4)
+        a = (0, 359, 0, 100, 0, 40 + 10 * t, 1 if (kind == "wo" and t == 1) else 0)
+        return xdm.RangeInArgsAlg(*a), oracle.RangeInArgs(*a)
+
+    items, expect, keep = [], [], []
+    for t in range(4):                                    # time-major: one frame of every stream per step
+        for si, (kind, codec, orc) in enumerate(streams):
+            fam = "blobs" if kind == "oo" else ("grid" if kind == "om" else "scene")
+            fr = synth.make_frame(fam, 100 * si + t, w, h, layout_of(kind))
+            ia, oia = args_for(kind, t)
+            oa = xdm.OUT_ARGS_ALG[xdm.KIND_OF[kind]]()
+            keep.append((fr, ia))
+            items.append((codec, fr, ia, oa, 5))
+            ok, exp = orc.process(fr, oia, seed=5)
+            assert ok == 1
+            expect.append((kind, ia, exp))
+    assert process_mixed(items) == 0
+    for (codec, fr, ia, oa, _), (kind, _, exp) in zip(items, expect):
+        if kind == "om":
+            n = ia.widthM * ia.heightN
+            assert list(oa.outColor[:n]) == list(exp.outColor[:n])
+        elif kind == "oo":
+            assert out_bytes(oa, 24) == out_bytes(exp, 24)
+        else:
+            assert out_bytes(oa) == out_bytes(exp), kind
+            if ia.autoDetectHsv:
+                assert detect_fields(oa) == detect_fields(exp)
+    for _, codec, _ in streams:
+        codec.close()
+
+
+@pytest.mark.parametrize("kind", ["ol", "oo"])
+def test_logical_streams_in_one_batch(kind):
+    """TRIKB200_Batch.streamIds: many logical streams through ONE handle and ONE launch; every stream carries
+    its own state (OL cross-band lag, OO persisting range) exactly like its own codec instance."""
+    w, h = 320, 240
+    nstreams, steps = 7, 4
+    codec = open_sensor(kind, w, h)
+    oracles = [oracle.OracleSensor(kind, w, h) for _ in range(nstreams)]
+    InAlg = xdm.IN_ARGS_ALG[xdm.KIND_OF[kind]]
+    for t in range(steps):                                 # several calls: the state persists across calls too
+        frames, ias, ids, exps = [], [], [], []
+        order = list(range(nstreams)) if t % 2 == 0 else list(reversed(range(nstreams)))
+        for sidx in order + order[:3]:                     # some streams twice within one batch
+            fam = "blobs" if kind == "oo" else "halves"
+            fr = synth.make_frame(fam, 10 * sidx + t, w, h, "yuv422p")
+            if kind == "oo":
+                a = (1, 0, 20 + sidx, 80, 20, 50, 30, 0) if (t == 0 or (sidx + t) % 3 == 0) else (0, 0, 0, 0, 0, 0, 0, 0)
+            else:
+                a = (0, 359, 0, 100, 0, 40 + sidx, 0)
+            frames.append(fr)
+            ias.append(InAlg(*a))
+            ids.append(sidx)
+            ok, exp = oracles[sidx].process(fr, oracle.IN_ARGS[kind](*a))
+            exps.append(exp)
+        arr = (InAlg * len(ias))(*ias)
+        ret, outs = codec.process_batch(np.stack(frames), arr, stream_ids=ids, num_streams=nstreams)
+        assert ret == 0
+        nb = 24 if kind == "oo" else 3
+        for o, e in zip(outs, exps):
+            assert out_bytes(o, nb) == out_bytes(e, nb), (kind, t)
+    codec.close()

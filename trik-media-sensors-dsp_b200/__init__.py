@@ -8,4 +8,4 @@ trikset/trik-media-sensors-dsp (webcam object/line sensors, ov7670 object/line/m
   synth.py   seeded synthetic camera frames shared by tests and bench
 """
 from . import xdm  # noqa: F401
-from .sensors import Codec, TrikB200Error, open_sensor, lib, launch_count, last_error  # noqa: F401
+from .sensors import Codec, TrikB200Error, open_sensor, lib, launch_count, last_error, process_mixed  # noqa: F401

@@ -109,6 +109,7 @@ struct Instance {
   Geometry     geo{};
   int          outWidth = 0, outHeight = 0, outLineLength = 0;
   CarriedState state;
+  std::vector<CarriedState> streamStates;   // logical streams of the batch extension (TRIKB200_Batch.streamIds)
   int64_t      seed = -1;
   cudaStream_t stream = nullptr;
 
@@ -224,6 +225,7 @@ bool instance_setup(Instance* in, int width, int height, int lineLength, int out
 {
   in->valid = false;
   in->state = CarriedState();
+  in->streamStates.clear();
   if (width < 0 || height < 0 || width % 32 != 0 || height % 4 != 0)
     return false;
   // OO: bitmap row offsets and labels are uint16 in the reference (cv_bitmap_builder_reference.hpp:93-96);
@@ -250,6 +252,25 @@ struct BatchView {
   const int64_t* seeds; bool seedsBroadcast;
   cudaStream_t   stream;
   bool           async;
+  // scattered form (trikb200_processMixed): one pointer per frame instead of base + stride
+  const int32_t* streamIds = nullptr; int numStreams = 0;
+  const uint8_t* const* framePtrs = nullptr;
+  const uint8_t* const* inPtrs = nullptr;
+  uint8_t* const*       outPtrs = nullptr;
+
+  const uint8_t* in_args(int i) const { return inPtrs ? inPtrs[i] : inArgs + (size_t)i * inStride; }
+  uint8_t* out_args(int i) const { return outPtrs ? outPtrs[i] : outArgs + (size_t)i * outStride; }
+  bool broadcast_in() const { return !inPtrs && inStride == 0; }
+};
+
+// what enqueue_batch leaves for finish_batch
+struct Pending {
+  cudaStream_t s = nullptr;
+  size_t recBytes = 0;
+  int numFlagged = 0;
+  bool hostTail = false;
+  int histBins = 0;
+  bool needsFinish = false;
 };
 
 size_t result_record_bytes(int kind)
@@ -324,7 +345,7 @@ void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, const uin
   }
 }
 
-bool run_batch(Instance* in, const BatchView& b)
+bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
 {
   if (!in->valid || in->geo.width <= 0 || in->geo.height <= 0)
   {
@@ -340,10 +361,10 @@ bool run_batch(Instance* in, const BatchView& b)
 
   // 0. argument checks that the reference leaves to undefined behaviour
   int maxRows = 0, maxCols = 0, numFlagged = 0;
-  const size_t nargs = (b.inStride == 0) ? 1 : (size_t)b.n;
+  const size_t nargs = b.broadcast_in() ? 1 : (size_t)b.n;
   for (size_t i = 0; i < nargs; ++i)
   {
-    const uint8_t* ia = b.inArgs + i * (size_t)b.inStride;
+    const uint8_t* ia = b.in_args((int)i);
     if (kind == KIND_OM)
     {
       const TRIKB200_MxnInArgsAlg* a = reinterpret_cast<const TRIKB200_MxnInArgsAlg*>(ia);
@@ -358,7 +379,7 @@ bool run_batch(Instance* in, const BatchView& b)
       if (N > maxCols) maxCols = N;
     }
     else if (wants_autodetect(kind, ia))
-      numFlagged += (b.inStride == 0) ? b.n : 1;
+      numFlagged += b.broadcast_in() ? b.n : 1;
   }
   const bool hostTail = numFlagged > 0 && kind != KIND_WO;
   if (hostTail && (b.async || b.outOnDevice))
@@ -369,18 +390,31 @@ bool run_batch(Instance* in, const BatchView& b)
   (void)inSize;
 
   // 1. per-frame parameters (carried state advances frame by frame, as n process() calls would)
-  const bool broadcast = (b.inStride == 0) && kind != KIND_OL && kind != KIND_OO;
+  const bool broadcast = b.broadcast_in() && kind != KIND_OL && kind != KIND_OO;
+  if (b.streamIds && (int)in->streamStates.size() < b.numStreams)
+    in->streamStates.resize((size_t)b.numStreams);
   const size_t np = broadcast ? 1 : (size_t)b.n;
   if (!in->grow_pinned(in->hParams, in->hParamsCap, np)) return false;
   if (!in->grow_device(in->dParams, in->dParamsCap, np, false)) return false;
   for (size_t i = 0; i < np; ++i)
-    prepare_frame_params(kind, in->geo, b.inArgs + i * (size_t)b.inStride, in->state, in->hParams[i]);
+    prepare_frame_params(kind, in->geo, b.in_args((int)i), b.streamIds ? in->streamStates[(size_t)b.streamIds[i]] : in->state, in->hParams[i]);
   CUDA_TRY(cudaMemcpyAsync(in->dParams, in->hParams, np * sizeof(FrameParams), cudaMemcpyHostToDevice, s));
 
   // 2. frames
   Geometry g = in->geo;
   const uint8_t* dFrames = b.frames;
-  if (b.framesOnDevice)
+  if (b.framePtrs)
+  {
+    // scattered frames: stage them one by one into the handle's device buffer
+    const size_t stride = (fbytes + 15u) & ~(size_t)15u;
+    if (!in->grow_device(in->dFrames, in->dFramesCap, stride * b.n, false)) return false;
+    for (int i = 0; i < b.n; ++i)
+      CUDA_TRY(cudaMemcpyAsync(in->dFrames + (size_t)i * stride, b.framePtrs[i], fbytes,
+                               b.framesOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    dFrames = in->dFrames;
+    g.frameStride = (int64_t)stride;
+  }
+  else if (b.framesOnDevice)
     g.frameStride = b.frameStride;
   else
   {
@@ -440,7 +474,7 @@ bool run_batch(Instance* in, const BatchView& b)
     if (!in->grow_device(in->dFlagged, in->dFlaggedCap, (size_t)numFlagged, false)) return false;
     int k = 0;
     for (int i = 0; i < b.n; ++i)
-      if (wants_autodetect(kind, b.inArgs + (size_t)i * b.inStride))
+      if (wants_autodetect(kind, b.in_args(i)))
         in->hFlagged[k++] = i;
     CUDA_TRY(cudaMemcpyAsync(in->dFlagged, in->hFlagged, sizeof(int) * numFlagged, cudaMemcpyHostToDevice, s));
     if (kind == KIND_WO)
@@ -472,7 +506,20 @@ bool run_batch(Instance* in, const BatchView& b)
   }
   if (!in->grow_pinned(in->hOut, in->hOutCap, recBytes * b.n)) return false;
   CUDA_TRY(cudaMemcpyAsync(in->hOut, dOut, recBytes * b.n, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  pend.s = s; pend.recBytes = recBytes; pend.numFlagged = numFlagged; pend.hostTail = hostTail;
+  pend.histBins = histBins; pend.needsFinish = true;
+  return true;
+}
+
+// wait for the stream, run the host tail (annealing) and merge the records into the caller's structs
+bool finish_batch(Instance* in, const BatchView& b, const Pending& pend)
+{
+  const int kind = in->kind;
+  const int numFlagged = pend.numFlagged, histBins = pend.histBins;
+  const bool hostTail = pend.hostTail;
+  const size_t recBytes = pend.recBytes;
+  CUDA_TRY(cudaSetDevice(in->device));
+  CUDA_TRY(cudaStreamSynchronize(pend.s));
 
   // 6. host tail: anneal the flagged frames (threads across frames), then merge
   std::vector<uint16_t> detect;
@@ -486,7 +533,8 @@ bool run_batch(Instance* in, const BatchView& b)
       {
         const int32_t* rec = in->hHist + (size_t)k * (histBins + 2);
         const int frame = in->hFlagged[k];
-        const unsigned seed = (unsigned)(b.seeds ? b.seeds[b.seedsBroadcast ? 0 : frame] : (int64_t)time(NULL));
+        const int64_t sd = b.seeds ? b.seeds[b.seedsBroadcast ? 0 : frame] : -1;
+        const unsigned seed = sd >= 0 ? (unsigned)sd : (unsigned)time(NULL);
         if (kind == KIND_OO)
           anneal_oo(rec, rec[histBins], seed, &detect[(size_t)6 * k]);
         else
@@ -505,13 +553,21 @@ bool run_batch(Instance* in, const BatchView& b)
   int k = 0;
   for (int i = 0; i < b.n; ++i)
   {
-    const uint8_t* ia = b.inArgs + (size_t)i * b.inStride;
+    const uint8_t* ia = b.in_args(i);
     const uint16_t* det = nullptr;
     if (hostTail && wants_autodetect(kind, ia))
       det = &detect[(size_t)6 * k++];
-    merge_result(kind, ia, in->hOut + (size_t)i * recBytes, det, b.outArgs + (size_t)i * b.outStride);
+    merge_result(kind, ia, in->hOut + (size_t)i * recBytes, det, b.out_args(i));
   }
   return true;
+}
+
+bool run_batch(Instance* in, const BatchView& b)
+{
+  Pending pend;
+  if (!enqueue_batch(in, b, pend))
+    return false;
+  return pend.needsFinish ? finish_batch(in, b, pend) : true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -987,7 +1043,90 @@ XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Bat
   b.seeds = batch->seeds; b.seedsBroadcast = false;
   b.stream = reinterpret_cast<cudaStream_t>(batch->stream);
   b.async = (batch->flags & TRIKB200_BATCH_ASYNC) != 0;
+  if (batch->streamIds)
+  {
+    if (batch->numStreams <= 0)
+    {
+      set_error("streamIds given but numStreams <= 0");
+      return IVIDTRANSCODE_EFAIL;
+    }
+    for (int i = 0; i < batch->numFrames; ++i)
+      if (batch->streamIds[i] < 0 || batch->streamIds[i] >= batch->numStreams)
+      {
+        set_error("streamIds entry out of range");
+        return IVIDTRANSCODE_EFAIL;
+      }
+    b.streamIds = batch->streamIds;
+    b.numStreams = batch->numStreams;
+  }
   return run_batch(in, b) ? IVIDTRANSCODE_EOK : IVIDTRANSCODE_EFAIL;
+}
+
+XDAS_Int32 trikb200_processMixed(const TRIKB200_MixedEntry* entries, XDAS_Int32 numEntries)
+{
+  if (numEntries < 0 || (numEntries > 0 && !entries))
+  {
+    set_error("null entries");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  // group by handle, keeping each handle's entries in order (carried state!)
+  struct Group {
+    TrikB200Handle* h;
+    std::vector<const uint8_t*> frames, ins;
+    std::vector<uint8_t*> outs;
+    std::vector<int64_t> seeds;
+    BatchView view{};
+    Pending pend;
+    bool enqueued = false;
+  };
+  std::vector<Group> groups;
+  for (int i = 0; i < numEntries; ++i)
+  {
+    const TRIKB200_MixedEntry& e = entries[i];
+    TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(e.handle);
+    if (!h || !instance_of(h) || !e.frame || !e.inArgsAlg || !e.outArgsAlg)
+    {
+      set_error("null pointer in a mixed entry");
+      return IVIDTRANSCODE_EFAIL;
+    }
+    Group* gptr = nullptr;
+    for (Group& g : groups)
+      if (g.h == h) { gptr = &g; break; }
+    if (!gptr)
+    {
+      groups.emplace_back();
+      gptr = &groups.back();
+      gptr->h = h;
+    }
+    gptr->frames.push_back(reinterpret_cast<const uint8_t*>(e.frame));
+    gptr->ins.push_back(reinterpret_cast<const uint8_t*>(e.inArgsAlg));
+    gptr->outs.push_back(reinterpret_cast<uint8_t*>(e.outArgsAlg));
+    gptr->seeds.push_back(e.seed);
+  }
+  // enqueue every handle's work on its own stream, then finish them all: the handles overlap on the GPU
+  bool ok = true;
+  for (Group& g : groups)
+  {
+    BatchView& b = g.view;
+    b.n = (int)g.frames.size();
+    b.framePtrs = g.frames.data(); b.inPtrs = g.ins.data(); b.outPtrs = g.outs.data();
+    b.framesOnDevice = false; b.outOnDevice = false;
+    b.inStride = (int)in_args_alg_size(g.h->kind); b.outStride = (int)out_args_alg_size(g.h->kind);
+    b.seeds = g.seeds.data(); b.seedsBroadcast = false;
+    b.stream = nullptr; b.async = false;
+    if ((instance_of(g.h)->geo.lineLength & 15) != 0)
+    {
+      set_error("inputLineLength must be a multiple of 16");
+      ok = false;
+      break;
+    }
+    g.enqueued = enqueue_batch(instance_of(g.h), b, g.pend);
+    if (!g.enqueued) { ok = false; break; }
+  }
+  for (Group& g : groups)
+    if (g.enqueued && g.pend.needsFinish)
+      ok = finish_batch(instance_of(g.h), g.view, g.pend) && ok;
+  return ok ? IVIDTRANSCODE_EOK : IVIDTRANSCODE_EFAIL;
 }
 
 XDAS_Int32 trikb200_synchronize(IVIDTRANSCODE_Handle handle)
@@ -1036,6 +1175,7 @@ XDAS_Int32 trikb200_setDevice(XDAS_Int32 device)
 int64_t trikb200_launchCount(void) { return launch_count(); }
 void trikb200_setSlabsPerFrame(XDAS_Int32 slabs) { g_slabsPerFrame = slabs; }
 void trikb200_setLoadStages(XDAS_Int32 stages) { set_sum_stages(stages); }
+void trikb200_setBlockThreads(XDAS_Int32 threads) { set_target_threads(threads); }
 const char* trikb200_lastError(void) { return t_lastError.c_str(); }
 
 /* test probes: exhaustive pixel functions straight from the device code (tests/test_pixel_gpu.py) */

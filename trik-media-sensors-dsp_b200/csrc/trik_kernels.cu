@@ -24,6 +24,8 @@ static long long g_launches = 0;
 //   WL: tuned line kernel, cp.async ring of 4;  OL: first-version kernel, ring of 2;  WO: register prefetch.
 // trikb200_setLoadStages(v): v % 100 = load path (0 register prefetch, 2 / 4 ring depth),
 //   v / 100 = 0 per-sensor default kernel, 1 force the first-version kernel, 2 force the tuned line kernel.
+static int g_targetThreads = 0;             // 0 = default (about 256 threads per CTA)
+void set_target_threads(int t) { g_targetThreads = t; }
 static int g_tuneStages = -1;
 static int g_tuneKernel = 0;
 static bool g_legacyLineKernel = false;      // resolved per launch
@@ -218,7 +220,8 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
     }
     else
     {
-      const int fillSlot = (int)((it + STAGES - 1) % STAGES);
+      constexpr int ST = STAGES > 0 ? STAGES : 1;
+      const int fillSlot = (int)((it + ST - 1) % ST);
       if (fillRow < r1)
       {
         cp_async16(&s_ring[(fillSlot * PLANES) * blockDim.x + t], fillPtr);
@@ -228,7 +231,7 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
       fillRow += rpi;
       fillPtr += rowStep;
       cp_async_wait<STAGES - 1>();
-      const int slot = (int)(it % STAGES);
+      const int slot = (int)(it % ST);
       cur = s_ring[(slot * PLANES) * blockDim.x + t];
       if (PLANAR) curC = s_ring[(slot * PLANES + 1) * blockDim.x + t];
     }
@@ -524,13 +527,14 @@ vsum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePar
     }
     else
     {
+      constexpr int ST = STAGES > 0 ? STAGES : 1;
       if (fillIt < iters)
-        request(&s_ring[((it + STAGES - 1) % STAGES) * blockDim.x + t], fillPtr);
+        request(&s_ring[((it + ST - 1) % ST) * blockDim.x + t], fillPtr);
       cp_async_commit();
       ++fillIt;
       fillPtr += rowStep;
       cp_async_wait<STAGES - 1>();
-      cur = s_ring[(it % STAGES) * blockDim.x + t];
+      cur = s_ring[(it % ST) * blockDim.x + t];
     }
 
     if (PLANAR)
@@ -634,7 +638,9 @@ int sum_sensor_block_threads(int kind, int width)
   const int cpr = width / sum_chunk_pixels(kind);
   if (cpr <= 0 || cpr > 1024)
     return 0;
-  int k = (256 + cpr - 1) / cpr;
+  // measured on B200 (profiles/r01e_tuning_cta_size.jsonl): CTAs of ~160 threads beat 320 at 160x120 and 320x240
+  const int target = g_targetThreads > 0 ? g_targetThreads : 128;
+  int k = (target + cpr - 1) / cpr;
   for (int j = 0; j < 16; ++j)
     if ((cpr * (k + j)) % 32 == 0 && cpr * (k + j) <= 1024)
     {

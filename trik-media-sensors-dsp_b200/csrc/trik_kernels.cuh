@@ -83,6 +83,7 @@ cudaError_t launch_probe_rgb2hsv(uint32_t first, uint32_t count, uint32_t* out, 
 
 int sum_sensor_block_threads(int kind, int width);
 void set_sum_stages(int stages);
+void set_target_threads(int threads);
 long long launch_count();
 
 } // namespace trikb200

@@ -39,12 +39,15 @@ def lib():
         l.trikb200_delete.argtypes = [C.c_void_p]
         l.trikb200_processBatch.argtypes = [C.c_void_p, C.POINTER(xdm.Batch)]
         l.trikb200_processBatch.restype = C.c_int32
+        l.trikb200_processMixed.argtypes = [C.c_void_p, C.c_int32]
+        l.trikb200_processMixed.restype = C.c_int32
         l.trikb200_synchronize.argtypes = [C.c_void_p]
         l.trikb200_setSeed.argtypes = [C.c_void_p, C.c_int64]
         l.trikb200_setDevice.argtypes = [C.c_int32]
         l.trikb200_launchCount.restype = C.c_int64
         l.trikb200_setSlabsPerFrame.argtypes = [C.c_int32]
         l.trikb200_setLoadStages.argtypes = [C.c_int32]
+        l.trikb200_setBlockThreads.argtypes = [C.c_int32]
         l.trikb200_lastError.restype = C.c_char_p
         l.trikb200_probePixels.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]
         for f in ("trikb200_sizeofInArgsAlg", "trikb200_sizeofOutArgsAlg", "trikb200_sizeofInArgs",
@@ -214,7 +217,7 @@ class Codec:
         return ret, oa
 
     def process_batch(self, frames, in_algs, out_algs=None, seeds=None, frames_device=False, frame_stride=None,
-                      num_frames=None, out_device_ptr=None, stream=None, flags=0):
+                      num_frames=None, out_device_ptr=None, stream=None, flags=0, stream_ids=None, num_streams=0):
         """n frames == n sequential process() calls.
 
         frames: (n, frame_bytes) uint8 numpy array, or a raw device pointer (int) with
@@ -250,6 +253,10 @@ class Codec:
             b.seeds = C.addressof(keep)
         b.stream = stream
         b.flags = flags
+        keep_ids = None
+        if stream_ids is not None:
+            keep_ids = (C.c_int32 * n)(*[int(x) for x in stream_ids])
+            b.streamIds, b.numStreams = C.addressof(keep_ids), int(num_streams)
         ret = self.lib.trikb200_processBatch(self.handle, C.byref(b))
         return ret, out_algs
 
@@ -281,3 +288,15 @@ def open_sensor(kind, width, height, line_length=None, out_w=None, out_h=None, d
     if c.set_params(width, height, line_length, out_w, out_h) != 0:
         raise TrikB200Error("control(XDM_SETPARAMS) rejected %dx%d" % (width, height))
     return c
+
+
+def process_mixed(items):
+    """items: list of (codec, frame ndarray, in_alg, out_alg, seed) -- one frame each, any mix of sensors.
+    Equivalent to calling codec.process() on every item in order (trikb200_processMixed)."""
+    n = len(items)
+    entries = (xdm.MixedEntry * n)()
+    for e, (codec, frame, ia, oa, seed) in zip(entries, items):
+        assert frame.dtype == np.uint8 and frame.flags["C_CONTIGUOUS"]
+        e.handle, e.frame = codec.handle, frame.ctypes.data
+        e.inArgsAlg, e.outArgsAlg, e.seed = C.addressof(ia), C.addressof(oa), -1 if seed is None else int(seed)
+    return lib().trikb200_processMixed(entries, n)

@@ -192,4 +192,10 @@ class Batch(C.Structure):
     _fields_ = [("size", C.c_int32), ("numFrames", C.c_int32), ("frames", C.c_void_p), ("frameStride", C.c_int64),
                 ("framesMem", C.c_int32), ("inArgsAlg", C.c_void_p), ("inArgsStride", C.c_int32),
                 ("outArgsAlg", C.c_void_p), ("outArgsStride", C.c_int32), ("outArgsMem", C.c_int32),
-                ("seeds", C.c_void_p), ("stream", C.c_void_p), ("flags", C.c_int32)]
+                ("seeds", C.c_void_p), ("stream", C.c_void_p), ("flags", C.c_int32),
+                ("streamIds", C.c_void_p), ("numStreams", C.c_int32)]
+
+
+class MixedEntry(C.Structure):
+    _fields_ = [("handle", C.c_void_p), ("frame", C.c_void_p), ("inArgsAlg", C.c_void_p), ("outArgsAlg", C.c_void_p),
+                ("seed", C.c_int64)]
