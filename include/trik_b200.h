@@ -148,7 +148,7 @@ typedef enum TRIKB200_Kind {
  *   ialg.algAlloc  (fxns.c:85-102)  2 records: {sizeof(handle), EXTERNAL, PERSIST}, {0x1000, DARAM0, PERSIST}
  *   ialg.algInit   (fxns.c:146-166) + creates the device buffers and the CUDA stream owned by the handle
  *   ialg.algFree   (fxns.c:114-136) returns the same two records with base filled
- *   process        (fxns.c:174-264) one frame, HOST buffers
+ *   process        (fxns.c:174-264) one frame, HOST buffers; writes the RGB565X preview with overlays into outBufs->bufs[0]
  *   control        (fxns.c:272-334) XDM_GETSTATUS/GETBUFINFO/SETPARAMS/RESET/SETDEFAULT/FLUSH/GETVERSION */
 extern IVIDTRANSCODE_Fxns TRIKB200_WO_FXNS;
 extern IVIDTRANSCODE_Fxns TRIKB200_WL_FXNS;
@@ -208,6 +208,10 @@ typedef struct TRIKB200_Batch {
                                   serves all streams.  NULL = one stream, the handle itself.  Stream states are reset
                                   by control(XDM_SETPARAMS) like the handle's own. */
     XDAS_Int32  numStreams;
+    void*       previews;      /* optional: RGB565X preview images with overlays, frame i at previews + i*previewStride,
+                                  each outputHeight * outputLineLength bytes as process() produces them; NULL = none */
+    int64_t     previewStride;
+    XDAS_Int32  previewsMem;   /* TRIKB200_MEM_* */
 } TRIKB200_Batch;
 
 /* n frames through one handle == n sequential process() calls (without the preview image).

@@ -187,12 +187,12 @@ def test_setparams_rebuilds_the_algorithm_object():
     c.close()
 
 
-def test_preview_is_zero_filled_and_reported():
-    """Until the preview image lands process() zero-fills it exactly as
-    vidtranscode_cv_fxns.c:234 does and reports bufSize = outHeight * outLineLength."""
+def test_preview_size_is_reported():
+    """process() reports bufSize = outHeight * outLineLength and zero-fills what lies beyond the image
+    (vidtranscode_cv_fxns.c:234,251)."""
     c = open_sensor("wl", 320, 240, out_w=160, out_h=120)
-    c.preview[:] = 0xAB
-    ret, oa = c.process(synth.make_frame("scene", 0, 320, 240, "yuyv"), xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 40, 0))
-    assert ret == 0 and not c.preview.any()
+    big = np.full(160 * 120 * 2 + 512, 0xAB, dtype=np.uint8)
+    ret, oa = c.process(synth.make_frame("scene", 0, 320, 240, "yuyv"), xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 40, 0), preview=big)
+    assert ret == 0 and not big[160 * 120 * 2:].any() and big[:160 * 120 * 2].any()
     assert oa.base.encodedBuf[0].bufSize == 120 * 160 * 2 and oa.base.bitsGenerated[0] == 120 * 160 * 2 * 8
     c.close()

@@ -124,6 +124,11 @@ struct Instance {
   uint16_t*    dEqual = nullptr;    size_t dEqualCap = 0;      // OO label equivalences
   int*         dFlagged = nullptr;  size_t dFlaggedCap = 0;    // indices of frames that auto-calibrate
   int32_t*     dHist = nullptr;     size_t dHistCap = 0;       // ordered +1/-2 histograms (int32 entries)
+  // preview (RGB565X) support: index maps of this geometry, overlay inputs, staging image
+  int32_t*     dHi2ho = nullptr;  int32_t* dWi2wo = nullptr;   // source row/col -> preview row/col
+  int32_t*     dLastRow = nullptr; int32_t* dLastCol = nullptr; // preview row/col -> last source row/col (-1: none)
+  DrawInfo*    dDraw = nullptr;     size_t dDrawCap = 0;
+  uint8_t*     dPreview = nullptr;  size_t dPreviewCap = 0;
   // pinned host staging
   FrameParams* hParams = nullptr;   size_t hParamsCap = 0;
   uint8_t*     hOut = nullptr;      size_t hOutCap = 0;
@@ -142,6 +147,9 @@ struct Instance {
     cudaFree(dAcc);    dAcc = nullptr;    dAccCap = 0;
     cudaFree(dOut);    dOut = nullptr;    dOutCap = 0;
     cudaFree(dMxnTable); dMxnTable = nullptr;
+    free_maps();
+    cudaFree(dDraw);    dDraw = nullptr;    dDrawCap = 0;
+    cudaFree(dPreview); dPreview = nullptr; dPreviewCap = 0;
     cudaFree(dBitmaps);  dBitmaps = nullptr;  dBitmapsCap = 0;
     cudaFree(dClusters); dClusters = nullptr; dClustersCap = 0;
     cudaFree(dEqual);    dEqual = nullptr;    dEqualCap = 0;
@@ -151,6 +159,41 @@ struct Instance {
     cudaFreeHost(hOut);     hOut = nullptr;     hOutCap = 0;
     cudaFreeHost(hFlagged); hFlagged = nullptr; hFlaggedCap = 0;
     cudaFreeHost(hHist);    hHist = nullptr;    hHistCap = 0;
+  }
+
+  void free_maps()
+  {
+    cudaFree(dHi2ho); cudaFree(dWi2wo); cudaFree(dLastRow); cudaFree(dLastCol);
+    dHi2ho = dWi2wo = dLastRow = dLastCol = nullptr;
+  }
+
+  // index maps of the preview: i * min(outW/W, outH/H) truncated, in double as the reference computes them
+  // (webcam/object_sensor/.../cv_ball_detector_seqpass.hpp:371-387), and their "last writer" inverses
+  bool build_maps()
+  {
+    free_maps();
+    const int W = geo.width, H = geo.height;
+    if (W <= 0 || H <= 0 || outWidth <= 0 || outHeight <= 0)
+      return true;
+    const double a = static_cast<double>(outWidth) / W, b = static_cast<double>(outHeight) / H;
+    const double shift = a < b ? a : b;
+    std::vector<int32_t> wi(W), hi(H), lastCol(outWidth, -1), lastRow(outHeight, -1);
+    for (int i = 0; i < W; ++i) wi[i] = (int32_t)(uint32_t)(i * shift);
+    for (int i = 0; i < H; ++i) hi[i] = (int32_t)(uint32_t)(i * shift);
+    // OL only writes source columns 5..W-5 (ov7670/line_sensor/.../cv_line_detector_seqpass.hpp:288)
+    const int c0 = kind == KIND_OL ? 5 : 0, c1 = kind == KIND_OL ? W - 5 : W - 1;
+    for (int i = c0; i <= c1; ++i) if (wi[i] < outWidth) lastCol[wi[i]] = i;
+    for (int i = 0; i < H; ++i) if (hi[i] < outHeight) lastRow[hi[i]] = i;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(&dWi2wo, sizeof(int32_t) * W));
+    CUDA_TRY(cudaMalloc(&dHi2ho, sizeof(int32_t) * H));
+    CUDA_TRY(cudaMalloc(&dLastCol, sizeof(int32_t) * outWidth));
+    CUDA_TRY(cudaMalloc(&dLastRow, sizeof(int32_t) * outHeight));
+    CUDA_TRY(cudaMemcpy(dWi2wo, wi.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dHi2ho, hi.data(), sizeof(int32_t) * H, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dLastCol, lastCol.data(), sizeof(int32_t) * outWidth, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dLastRow, lastRow.data(), sizeof(int32_t) * outHeight, cudaMemcpyHostToDevice));
+    return true;
   }
 
   bool init_device()
@@ -237,6 +280,9 @@ bool instance_setup(Instance* in, int width, int height, int lineLength, int out
   in->geo.lineLength = lineLength;
   in->geo.frameStride = 0;
   in->outWidth = outW; in->outHeight = outH; in->outLineLength = outLine;
+  in->geo.drawInfo = nullptr;
+  if (!in->build_maps())
+    return false;
   in->valid = true;
   return true;
 }
@@ -254,6 +300,7 @@ struct BatchView {
   bool           async;
   // scattered form (trikb200_processMixed): one pointer per frame instead of base + stride
   const int32_t* streamIds = nullptr; int numStreams = 0;
+  uint8_t* previews = nullptr; int64_t previewStride = 0; bool previewsOnDevice = false;
   const uint8_t* const* framePtrs = nullptr;
   const uint8_t* const* inPtrs = nullptr;
   uint8_t* const*       outPtrs = nullptr;
@@ -428,6 +475,21 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
     g.frameStride = (int64_t)stride;
   }
 
+  // preview wanted: the result tails also leave their source-coordinate values for the overlays
+  const bool wantPreview = b.previews != nullptr && in->outWidth > 0 && in->outHeight > 0 && in->dLastRow != nullptr;
+  const size_t previewBytes = (size_t)in->outHeight * in->outLineLength;
+  g.drawInfo = nullptr;
+  if (wantPreview)
+  {
+    if (in->outLineLength < in->outWidth * 2)
+    {
+      set_error("outputLineLength smaller than outputWidth * 2");
+      return false;
+    }
+    if (!in->grow_device(in->dDraw, in->dDrawCap, (size_t)b.n, true)) return false;
+    g.drawInfo = in->dDraw;
+  }
+
   // 3. the per-pixel kernels
   uint8_t* dOut;
   const bool directOut = b.outOnDevice && b.outStride == (int)recBytes && kind != KIND_OM;
@@ -487,6 +549,26 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       CUDA_TRY(launch_ordered_hist(kind, g, numFlagged, dFrames, in->dFlagged, in->dHist, s));
       CUDA_TRY(cudaMemcpyAsync(in->hHist, in->dHist, words * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
+  }
+
+  // 4b. preview image: base layer gather + overlays, then to the caller
+  if (wantPreview)
+  {
+    uint8_t* dPrev = b.previews;
+    long long pstrideBytes = b.previewStride;
+    if (!b.previewsOnDevice)
+    {
+      if (!in->grow_device(in->dPreview, in->dPreviewCap, previewBytes * b.n, false)) return false;
+      dPrev = in->dPreview;
+      pstrideBytes = (long long)previewBytes;
+    }
+    if (in->outLineLength > in->outWidth * 2)      // row padding is not produced by the kernels: keep it zero
+      CUDA_TRY(cudaMemset2DAsync(dPrev, (size_t)pstrideBytes, 0, previewBytes, b.n, s));
+    CUDA_TRY(launch_preview(kind, g, b.n, dFrames, in->dParams, pstride, in->dBitmaps, in->dDraw,
+                            reinterpret_cast<const int32_t*>(dOut), in->outWidth, in->outHeight, in->outLineLength,
+                            in->dLastRow, in->dLastCol, in->dHi2ho, in->dWi2wo, dPrev, pstrideBytes, s));
+    if (!b.previewsOnDevice)
+      CUDA_TRY(cudaMemcpy2DAsync(b.previews, (size_t)b.previewStride, dPrev, previewBytes, previewBytes, b.n, cudaMemcpyDeviceToHost, s));
   }
 
   // 5. results
@@ -787,6 +869,10 @@ XDAS_Int32 vid_process(int kind, IVIDTRANSCODE_Handle algHandle, XDM1_BufDesc* i
       int64_t seed = in->seed >= 0 ? in->seed : (int64_t)time(NULL);
       b.seeds = &seed; b.seedsBroadcast = true;
       b.stream = nullptr; b.async = false;
+      if (outPtr != NULL && outSize > 0)
+      {
+        b.previews = reinterpret_cast<uint8_t*>(outPtr); b.previewStride = outSize; b.previewsOnDevice = false;
+      }
       ok = run_batch(in, b);
     }
     else
@@ -1043,6 +1129,18 @@ XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Bat
   b.seeds = batch->seeds; b.seedsBroadcast = false;
   b.stream = reinterpret_cast<cudaStream_t>(batch->stream);
   b.async = (batch->flags & TRIKB200_BATCH_ASYNC) != 0;
+  if (batch->previews)
+  {
+    const long long need = (long long)in->outHeight * in->outLineLength;
+    if (batch->numFrames > 1 && batch->previewStride < need)
+    {
+      set_error("previewStride smaller than outputHeight * outputLineLength");
+      return IVIDTRANSCODE_EFAIL;
+    }
+    b.previews = reinterpret_cast<uint8_t*>(batch->previews);
+    b.previewStride = batch->previewStride > 0 ? batch->previewStride : need;
+    b.previewsOnDevice = (batch->previewsMem == TRIKB200_MEM_DEVICE);
+  }
   if (batch->streamIds)
   {
     if (batch->numStreams <= 0)

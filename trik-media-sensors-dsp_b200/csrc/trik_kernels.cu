@@ -47,7 +47,8 @@ static void resolve_tuning(int kind)
 }
 extern long long g_launches_grid;
 extern long long g_launches_detect;
-long long launch_count() { return g_launches + g_launches_grid + g_launches_detect; }
+extern long long g_launches_preview;
+long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview; }
 
 // ---------------------------------------------------------------------------------------------
 // per-pair work
@@ -79,10 +80,12 @@ __device__ __forceinline__ uint32_t hsvfail_pair(uint32_t yy, uint32_t cw, const
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
 __device__ void finalize_sum(const Geometry& g, const FrameParams& p, uint32_t fails, uint32_t sxFail,
-                             uint32_t syFail, uint32_t crossFail, TargetOut* o)
+                             uint32_t syFail, uint32_t crossFail, TargetOut* o, const TargetOut* outBase)
 {
   const uint32_t W = (uint32_t)g.width, H = (uint32_t)g.height;
   TargetOut r;
+  DrawInfo di;
+  di.v[0] = 0; di.v[1] = 0; di.v[2] = 0; di.v[3] = 0;
   r.targetX = 0; r.targetY = 0; r.targetSize = 0; r.pad = 0;
   r.detectHue = r.detectHueTolerance = r.detectSat = r.detectSatTolerance = r.detectVal = r.detectValTolerance = 0;
   if (KIND == KIND_WO)
@@ -98,6 +101,7 @@ __device__ void finalize_sum(const Geometry& g, const FrameParams& p, uint32_t f
       r.targetX = (int8_t)(((tx - (int32_t)W / 2) * 100 * 2) / (int32_t)W);
       r.targetY = (int8_t)(((ty - (int32_t)H / 2) * 100 * 2) / (int32_t)H);
       r.targetSize = (uint8_t)((uint32_t)(radius * 100u * 4u) / (uint32_t)(W + H));
+      di.v[0] = 1; di.v[1] = tx; di.v[2] = ty; di.v[3] = (int32_t)radius;
     }
   }
   else
@@ -122,9 +126,15 @@ __device__ void finalize_sum(const Geometry& g, const FrameParams& p, uint32_t f
       if (ol)
         r.targetY = (int8_t)(int32_t)((uint32_t)(cross * 100u) / (uint32_t)(W * 2u * 40u));
       r.targetSize = (uint8_t)((uint32_t)(points * 100u) / (uint32_t)(H * W));
+      di.v[0] = 1; di.v[1] = tx;
     }
   }
   *o = r;
+  if (g.drawInfo)
+  {
+    int32_t* dv = static_cast<DrawInfo*>(g.drawInfo)[o - outBase].v;
+    dv[0] = di.v[0]; dv[1] = di.v[1]; dv[2] = di.v[2]; dv[3] = di.v[3];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,7 +350,7 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
         }
       }
       if (last)
-        finalize_sum<KIND>(g, p, a, b, c, d, out + frame);
+        finalize_sum<KIND>(g, p, a, b, c, d, out + frame, out);
     }
   }
 }
@@ -624,8 +634,8 @@ vsum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePar
       }
       if (last)
       {
-        if (PLANAR) finalize_sum<KIND_OL>(g, p, a, b, 0u, d, out + frame);
-        else        finalize_sum<KIND_WL>(g, p, a, b, 0u, 0u, out + frame);
+        if (PLANAR) finalize_sum<KIND_OL>(g, p, a, b, 0u, d, out + frame, out);
+        else        finalize_sum<KIND_WL>(g, p, a, b, 0u, 0u, out + frame, out);
       }
     }
   }

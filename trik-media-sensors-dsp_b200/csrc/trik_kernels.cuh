@@ -14,7 +14,15 @@ struct Geometry {
   int32_t width, height;      // pixels; width % 32 == 0, height % 4 == 0
   int32_t lineLength;         // byte stride of a row (of each plane for YUV422P)
   int64_t frameStride;        // bytes between frames of a batch
+  void*   drawInfo;           // DrawInfo[numFrames] for the preview overlays, or NULL when no preview is wanted
 };
+
+// What the overlay pass needs from the result tails, in SOURCE image coordinates (the OutArgs hold the
+// same quantities only after the lossy scaling to -100..100):
+//   WO      v[0] = points > 0,  v[1] = targetX, v[2] = targetY, v[3] = radius
+//   WL, OL  v[0] = points > 10, v[1] = targetX
+//   OO      v[0] = bit i set if target i is reported, v[1+2i], v[2+2i] = its x, y
+struct DrawInfo { int32_t v[20]; };
 
 // Per-frame parameters, prepared on the host from InArgsAlg + the handle's carried state.
 struct FrameParams {
@@ -76,6 +84,13 @@ cudaError_t launch_wo_detect(const Geometry& g, int numFlagged, const uint8_t* f
 // (bins = 256 for WL/OL, 1024 = 32x32 (H>>3, S>>3) for OO)
 cudaError_t launch_ordered_hist(int kind, const Geometry& g, int numFlagged, const uint8_t* frames, const int* frameIdx,
                                 int32_t* results, cudaStream_t stream);
+
+// RGB565X preview with overlays (trik_kernels_preview.cu); maps are device arrays prepared by the host
+cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
+                           int paramStride, const uint16_t* bitmaps, const DrawInfo* draw, const int32_t* omColours,
+                           int outW, int outH, int outLine, const int32_t* lastRow, const int32_t* lastCol,
+                           const int32_t* hi2ho, const int32_t* wi2wo, uint8_t* previews, long long previewStride,
+                           cudaStream_t stream);
 
 // exhaustive pixel-function probes for the parity tests: out[i] for i = blockIdx*blockDim+threadIdx
 cudaError_t launch_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);

@@ -517,6 +517,8 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
   r.detectHue = r.detectHueTolerance = r.detectSat = r.detectSatTolerance = r.detectVal = r.detectValTolerance = 0;
   bool noObjects = true;
   const int W = g.width, H = g.height;
+  DrawInfo di;
+  for (int i = 0; i < 20; ++i) di.v[i] = 0;
   for (int i = 0; i < 8; ++i)                             // cv_ball_detector_seqpass.hpp:572-590
   {
     // slots past the last label: the reference reads beyond its vector (undefined); defined here as empty
@@ -532,8 +534,11 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
       r.t[3 * i + 2] = (int8_t)(uint8_t)size;
       r.t[3 * i + 0] = (int8_t)(((x - W / 2) * 100 * 2) / W);
       r.t[3 * i + 1] = (int8_t)(((y - H / 2) * 100 * 2) / H);
+      di.v[0] |= 1 << i; di.v[1 + 2 * i] = x; di.v[2 + 2 * i] = y;
     }
   }
+  if (g.drawInfo)
+    static_cast<DrawInfo*>(g.drawInfo)[frame] = di;
   if (noObjects)
   {
     r.t[0] = 0; r.t[1] = 0; r.t[2] = 0;

@@ -217,7 +217,8 @@ class Codec:
         return ret, oa
 
     def process_batch(self, frames, in_algs, out_algs=None, seeds=None, frames_device=False, frame_stride=None,
-                      num_frames=None, out_device_ptr=None, stream=None, flags=0, stream_ids=None, num_streams=0):
+                      num_frames=None, out_device_ptr=None, stream=None, flags=0, stream_ids=None, num_streams=0,
+                      previews=None, previews_device_ptr=None, preview_stride=None):
         """n frames == n sequential process() calls.
 
         frames: (n, frame_bytes) uint8 numpy array, or a raw device pointer (int) with
@@ -253,6 +254,11 @@ class Codec:
             b.seeds = C.addressof(keep)
         b.stream = stream
         b.flags = flags
+        if previews is not None:
+            assert previews.dtype == np.uint8 and previews.ndim == 2 and previews.flags["C_CONTIGUOUS"]
+            b.previews, b.previewStride, b.previewsMem = previews.ctypes.data, previews.strides[0], xdm.MEM_HOST
+        elif previews_device_ptr is not None:
+            b.previews, b.previewStride, b.previewsMem = int(previews_device_ptr), int(preview_stride), xdm.MEM_DEVICE
         keep_ids = None
         if stream_ids is not None:
             keep_ids = (C.c_int32 * n)(*[int(x) for x in stream_ids])

@@ -193,7 +193,8 @@ class Batch(C.Structure):
                 ("framesMem", C.c_int32), ("inArgsAlg", C.c_void_p), ("inArgsStride", C.c_int32),
                 ("outArgsAlg", C.c_void_p), ("outArgsStride", C.c_int32), ("outArgsMem", C.c_int32),
                 ("seeds", C.c_void_p), ("stream", C.c_void_p), ("flags", C.c_int32),
-                ("streamIds", C.c_void_p), ("numStreams", C.c_int32)]
+                ("streamIds", C.c_void_p), ("numStreams", C.c_int32),
+                ("previews", C.c_void_p), ("previewStride", C.c_int64), ("previewsMem", C.c_int32)]
 
 
 class MixedEntry(C.Structure):
