@@ -260,7 +260,9 @@ const char* trikb200_lastError(void);
 
 /* diagnostics for the parity tests: run the DEVICE pixel functions over a range of inputs.
  * which = 0: index = Y | U<<8 | V<<16 -> 0x00RRGGBB (bit 31 set if the YUYV and YUV422P lane
- * paths disagree); which = 1: index = 0x00RRGGBB -> 0x00VVSSHH.  hostOut holds count words. */
+ * paths disagree); which = 1: index = 0x00RRGGBB -> 0x00VVSSHH (scalar form); which = 2: index = Y | U<<8 | V<<16
+ * -> 0x00VVSSHH through the packed two-pixel path the sensors use (bit 31: lane paths disagree).
+ * hostOut holds count words. */
 XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count, uint32_t* hostOut);
 
 #ifdef __cplusplus

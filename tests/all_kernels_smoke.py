@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Small run of EVERY kernel (all sensors, auto-detect, preview, slabs > 1, logical streams) for
-`compute-sanitizer --tool memcheck|racecheck python tools/sanitize_smoke.py`; also checks the oracle."""
+"""TEST HELPER: a small run of EVERY kernel (all sensors, auto-detect, preview, several CTAs per frame)
+checked against the oracle; usable stand-alone (`python tests/all_kernels_smoke.py`, e.g. under a
+sanitizer where one is available) and from tests/test_all_kernels_gpu.py."""
 import os
 import sys
 

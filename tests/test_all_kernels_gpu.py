@@ -13,9 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_every_kernel_small():
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import sanitize_smoke
-    sanitize_smoke.main()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import all_kernels_smoke
+    all_kernels_smoke.main()
 
 
 @pytest.mark.parametrize("kind", ["wl", "wo", "ol", "oo", "om"])

@@ -1282,7 +1282,8 @@ XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count
   uint32_t* d = nullptr;
   if (cudaMalloc(&d, (size_t)count * 4) != cudaSuccess)
     return IVIDTRANSCODE_EFAIL;
-  cudaError_t e = which == 0 ? launch_probe_yuv2rgb(first, count, d, 0) : launch_probe_rgb2hsv(first, count, d, 0);
+  cudaError_t e = which == 0 ? launch_probe_yuv2rgb(first, count, d, 0)
+                : (which == 1 ? launch_probe_rgb2hsv(first, count, d, 0) : launch_probe_yuv2hsv(first, count, d, 0));
   if (e == cudaSuccess)
     e = cudaMemcpy(hostOut, d, (size_t)count * 4, cudaMemcpyDeviceToHost);
   cudaFree(d);

@@ -229,13 +229,18 @@ int line_increment(GlibcRand& rng, int val, int mn, int mx, double base, double 
   }
 }
 
-int64_t line_F(const int32_t* h, uint8_t v0, uint8_t v1)  // :133-159, empty bin = -K0 = -1
-{
-  int64_t res = 0;
-  for (int v = v0; v <= v1; v++)
-    res += h[v] != 0 ? h[v] : -1;
-  return res;
-}
+// F (:133-159): sum over v0..v1 of (bin != 0 ? bin : -K0), K0 = 1.  The 9200 evaluations per frame only
+// differ in their bounds, so they are answered from an exact int64 prefix sum instead of a 256-step loop.
+struct LinePrefix {
+  int64_t p[257];
+  explicit LinePrefix(const int32_t* h)
+  {
+    p[0] = 0;
+    for (int v = 0; v < 256; ++v)
+      p[v + 1] = p[v] + (h[v] != 0 ? h[v] : -1);
+  }
+  int64_t F(uint8_t v0, uint8_t v1) const { return v0 <= v1 ? p[v1 + 1] - p[v0] : 0; }
+};
 
 // getIncrement (OO/.../cv_hsv_range_detector.hpp:77-98): half-open upper bound
 int oo_increment(GlibcRand& rng, int val, int mn, int mx, double t)
@@ -255,26 +260,27 @@ int oo_increment(GlibcRand& rng, int val, int mn, int mx, double t)
 
 int oo_truncate_hue(int v) { int r = v % 32; if (r < 0) r += 32; return r; }
 
-int64_t oo_foo(const int32_t* hs, int h1, int h2, int s1, int s2)   // m_foo :109-153, empty cell = -K0 = -2
-{
-  int64_t res = 0;
-  if (h1 <= h2)
+// m_foo (:109-153): sum over the hue x saturation rectangle (hue wraps when h1 > h2) of
+// (cell != 0 ? cell : -K0), K0 = 2; answered from an exact int64 summed-area table.
+struct HsPrefix {
+  int64_t sat[33][33];
+  explicit HsPrefix(const int32_t* hs)
   {
-    for (int h = h1; h <= h2; h++)
-      for (int s = s1; s <= s2; s++)
-        res += hs[h * 32 + s] != 0 ? hs[h * 32 + s] : -2;
+    for (int i = 0; i <= 32; ++i) sat[i][0] = sat[0][i] = 0;
+    for (int h = 0; h < 32; ++h)
+      for (int s = 0; s < 32; ++s)
+        sat[h + 1][s + 1] = sat[h][s + 1] + sat[h + 1][s] - sat[h][s] + (hs[h * 32 + s] != 0 ? hs[h * 32 + s] : -2);
   }
-  else
+  int64_t rect(int ha, int hb, int s1, int s2) const          // hue rows ha..hb, sat columns s1..s2, inclusive
   {
-    for (int h = h1; h < 32; h++)
-      for (int s = s1; s <= s2; s++)
-        res += hs[h * 32 + s] != 0 ? hs[h * 32 + s] : -2;
-    for (int h = 0; h <= h2; h++)
-      for (int s = s1; s <= s2; s++)
-        res += hs[h * 32 + s] != 0 ? hs[h * 32 + s] : -2;
+    if (ha > hb || s1 > s2) return 0;
+    return sat[hb + 1][s2 + 1] - sat[ha][s2 + 1] - sat[hb + 1][s1] + sat[ha][s1];
   }
-  return res;
-}
+  int64_t foo(int h1, int h2, int s1, int s2) const
+  {
+    return h1 <= h2 ? rect(h1, h2, s1, s2) : rect(h1, 31, s1, s2) + rect(0, h2, s1, s2);
+  }
+};
 
 } // namespace
 
@@ -283,7 +289,8 @@ void anneal_line(const int32_t hist[256], int seedBin, bool isOL, unsigned seed,
   GlibcRand rng;
   rng.seed(seed);
   uint8_t v0 = (uint8_t)seedBin, v1 = (uint8_t)seedBin;
-  int64_t L = line_F(hist, v0, v1);
+  const LinePrefix pre(hist);
+  int64_t L = pre.F(v0, v1);
   double T = 150;
   while (T > kTEnd)
   {
@@ -292,7 +299,7 @@ void anneal_line(const int32_t hist[256], int seedBin, bool isOL, unsigned seed,
       const double base = 1 + 1 / T;
       const uint8_t n0 = (uint8_t)line_increment(rng, v0, 0, 255, base, T);
       const uint8_t n1 = (uint8_t)line_increment(rng, v1, 0, 255, base, T);
-      const int64_t newL = line_F(hist, n0, n1);
+      const int64_t newL = pre.F(n0, n1);
       if (rng.next() <= std::pow(kE, (newL - L) / T) * kRandMax)
       {
         v0 = n0; v1 = n1; L = newL;
@@ -313,7 +320,8 @@ void anneal_oo(const int32_t hs[1024], int seedBin, unsigned seed, uint16_t out[
   rng.seed(seed);
   const int sMax = seedBin & 31;
   int h1 = seedBin >> 5, h2 = seedBin >> 5, s1 = sMax, s2 = sMax;
-  int64_t L = oo_foo(hs, h1, h2, s1, s2);
+  const HsPrefix pre(hs);
+  int64_t L = pre.foo(h1, h2, s1, s2);
   double T = 150;
   while (T > kTEnd)
   {
@@ -323,7 +331,7 @@ void anneal_oo(const int32_t hs[1024], int seedBin, unsigned seed, uint16_t out[
       const int h2n = oo_truncate_hue(oo_increment(rng, h2, 0, 32, T));
       const int s1n = oo_increment(rng, s1, 0, sMax, T);
       const int s2n = oo_increment(rng, s2, sMax, 32, T);
-      const int64_t Ln = oo_foo(hs, h1n, h2n, s1n, s2n);
+      const int64_t Ln = pre.foo(h1n, h2n, s1n, s2n);
       if (L < Ln || (rng.next() / kRandMax) <= std::pow(kE, -(L - Ln) / T))
       {
         h1 = h1n; h2 = h2n; s1 = s1n; s2 = s2n; L = Ln;

@@ -68,10 +68,10 @@ __device__ __forceinline__ uint32_t vfail_pair(uint32_t yy, uint32_t cw, const C
 }
 
 __device__ __forceinline__ uint32_t hsvfail_pair(uint32_t yy, uint32_t cw, const ChromaCoef coef,
-                                                 const uint16_t* lut43, const uint16_t* lut255,
-                                                 uint32_t from, uint32_t to, uint32_t expected)
+                                                 const HueLutEntry* lutHue, const uint16_t* lut255,
+                                                 const HsvBounds& bd, uint32_t expected)
 {
-  const uint32_t det = detect_pair_bits(yy, cw, coef, lut43, lut255, from, to, expected);
+  const uint32_t det = detect_pair_bits(yy, cw, coef, lutHue, lut255, bd, expected);
   return ((det & 1u) ^ 1u) | (((det >> 1) ^ 1u) << 16);
 }
 
@@ -152,6 +152,7 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
            const int slabs, const int rowsPerSlab, const int cpr, const int rpi)
 {
   constexpr bool PLANAR = (KIND == KIND_OL);
+  __shared__ HueLutEntry s_lutHue[256];
   __shared__ uint16_t s_lut43[256];
   __shared__ uint16_t s_lut255[256];
   __shared__ uint32_t s_red[32][4];
@@ -166,8 +167,10 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
   if (KIND == KIND_WO)
   {
     fill_div_luts(s_lut43, s_lut255);
+    fill_hue_lut(s_lutHue);
     __syncthreads();
   }
+  const HsvBounds bd = make_bounds(p.from, p.to);
 
   const int r0 = slab * rowsPerSlab;
   const int r1 = min(r0 + rowsPerSlab, g.height);
@@ -256,7 +259,7 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
         const uint32_t yy = w[k] & 0x00FF00FFu;
         uint32_t fl;
         if (KIND == KIND_WO)
-          fl = hsvfail_pair(yy, w[k], coef_yuyv(), s_lut43, s_lut255, p.from, p.to, p.expected);
+          fl = hsvfail_pair(yy, w[k], coef_yuyv(), s_lutHue, s_lut255, bd, p.expected);
         else
           fl = vfail_pair(yy, w[k], coef_yuyv(), p.negKlo2, p.n2);
         Sc += fl;
@@ -786,6 +789,36 @@ __global__ void probe_rgb2hsv_kernel(uint32_t first, uint32_t count, uint32_t* _
   const uint32_t rgb = first + i;
   out[i] = hsv_from_rgb8((int32_t)((rgb >> 16) & 0xFFu), (int32_t)((rgb >> 8) & 0xFFu), (int32_t)(rgb & 0xFFu),
                          s_lut43, s_lut255);
+}
+
+// packed pair path: index = Y | U << 8 | V << 16 -> 0x00VVSSHH through hsv_pair(); the probe pixel sits in
+// lane 0 of a YUYV word and in lane 1 of a YUV422P pair, both must agree (bit 31 flags a disagreement)
+__global__ void probe_yuv2hsv_kernel(uint32_t first, uint32_t count, uint32_t* __restrict__ out)
+{
+  __shared__ HueLutEntry s_lutHue[256];
+  __shared__ uint16_t s_lut43[256];
+  __shared__ uint16_t s_lut255[256];
+  fill_div_luts(s_lut43, s_lut255);
+  fill_hue_lut(s_lutHue);
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t idx = first + i;
+  const uint32_t y = idx & 0xFFu, u = (idx >> 8) & 0xFFu, v = (idx >> 16) & 0xFFu;
+  const uint32_t word = y | (u << 8) | ((255u - y) << 16) | (v << 24);
+  uint32_t a0, a1, b0, b1;
+  hsv_pair(word & 0x00FF00FFu, word, coef_yuyv(), s_lutHue, s_lut255, a0, a1);
+  const uint32_t cw = v | (u << 8) | (v << 16) | (u << 24);
+  hsv_pair(((255u - y) & 0xFFu) | (y << 16), cw, coef_planar1(), s_lutHue, s_lut255, b0, b1);
+  out[i] = a0 | ((a0 != b1 || a1 != b0) ? 0x80000000u : 0u);
+}
+
+cudaError_t launch_probe_yuv2hsv(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream)
+{
+  if (!count) return cudaSuccess;
+  probe_yuv2hsv_kernel<<<(count + 255u) / 256u, 256, 0, stream>>>(first, count, out);
+  ++g_launches;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream)

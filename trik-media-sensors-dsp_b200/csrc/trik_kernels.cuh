@@ -95,6 +95,7 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
 // exhaustive pixel-function probes for the parity tests: out[i] for i = blockIdx*blockDim+threadIdx
 cudaError_t launch_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
 cudaError_t launch_probe_rgb2hsv(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
+cudaError_t launch_probe_yuv2hsv(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
 
 int sum_sensor_block_threads(int kind, int width);
 void set_sum_stages(int stages);

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256)
 wo_detect_kernel(const Geometry g, const uint8_t* __restrict__ frames, const int* __restrict__ frameIdx,
                  TargetOut* __restrict__ out, const int left, const int right, const int top, const int bot)
 {
+  __shared__ HueLutEntry s_lutHue[256];
   __shared__ uint16_t s_lut43[256];
   __shared__ uint16_t s_lut255[256];
   __shared__ uint32_t s_cnt[3][256];
@@ -43,6 +44,7 @@ wo_detect_kernel(const Geometry g, const uint8_t* __restrict__ frames, const int
   const int t = threadIdx.x;
   const int frame = frameIdx[blockIdx.x];
   fill_div_luts(s_lut43, s_lut255);
+  fill_hue_lut(s_lutHue);
   for (int i = t; i < 3 * 256; i += blockDim.x)
   {
     (&s_cnt[0][0])[i] = 0u;
@@ -64,7 +66,7 @@ wo_detect_kernel(const Geometry g, const uint8_t* __restrict__ frames, const int
       const int row = r0 + i / pairs, pr = p0 + i % pairs;
       const uint32_t w = *reinterpret_cast<const uint32_t*>(base + (size_t)row * g.lineLength + (size_t)pr * 4u);
       uint32_t hsv[2];
-      hsv_pair(w & 0x00FF00FFu, w, coef_yuyv(), s_lut43, s_lut255, hsv[0], hsv[1]);
+      hsv_pair(w & 0x00FF00FFu, w, coef_yuyv(), s_lutHue, s_lut255, hsv[0], hsv[1]);
 #pragma unroll
       for (int e = 0; e < 2; ++e)
       {
@@ -131,6 +133,7 @@ ordered_hist_kernel(const Geometry g, const uint8_t* __restrict__ frames, const 
   constexpr bool PLANAR = (KIND != KIND_WL);
   constexpr int BINS = OO ? 1024 : 256;
   constexpr int PER = BINS / 256;                          // bins per thread in the update step
+  __shared__ HueLutEntry s_lutHue[OO ? 256 : 1];
   __shared__ uint16_t s_lut43[256];
   __shared__ uint16_t s_lut255[256];
   __shared__ int32_t  s_base[BINS];
@@ -140,7 +143,7 @@ ordered_hist_kernel(const Geometry g, const uint8_t* __restrict__ frames, const 
 
   const int t = threadIdx.x;
   const int frame = frameIdx[blockIdx.x];
-  if (OO) fill_div_luts(s_lut43, s_lut255);
+  if (OO) { fill_div_luts(s_lut43, s_lut255); fill_hue_lut(s_lutHue); }
   for (int i = t; i < BINS; i += 256)
   {
     s_base[i] = 0; s_nl[i] = 0; s_p[i] = 0; s_nr[i] = 0; s_last[i] = 0;
@@ -178,7 +181,7 @@ ordered_hist_kernel(const Geometry g, const uint8_t* __restrict__ frames, const 
       if (OO)
       {
         uint32_t h0, h1;
-        hsv_pair(yy, cw, coef, s_lut43, s_lut255, h0, h1);
+        hsv_pair(yy, cw, coef, s_lutHue, s_lut255, h0, h1);
         bin[0] = (((h0 & 0xFFu) >> 3) << 5) | (((h0 >> 8) & 0xFFu) >> 3);
         bin[1] = (((h1 & 0xFFu) >> 3) << 5) | (((h1 >> 8) & 0xFFu) >> 3);
       }

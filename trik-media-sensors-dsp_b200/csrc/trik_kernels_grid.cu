@@ -23,6 +23,17 @@ namespace trikb200 {
 extern long long g_launches_grid;
 long long g_launches_grid = 0;
 
+// threads per CTA = chunksPerRow * rowsPerIteration, about `target` threads, a multiple of 32 when possible
+static int rows_per_iteration(int cpr, int target)
+{
+  int k = (target + cpr - 1) / cpr;
+  for (int j = 0; j < 16; ++j)
+    if ((cpr * (k + j)) % 32 == 0 && cpr * (k + j) <= 1024)
+      return k + j;
+  if (cpr * k > 1024) k = 1024 / cpr;
+  return k < 1 ? 1 : k;
+}
+
 // =============================================================================================
 // OM
 // =============================================================================================
@@ -35,6 +46,7 @@ om_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParam
           const int maxGridRows, const int cpr, const int rpi)
 {
   extern __shared__ uint32_t s_dyn[];                     // [group][512] counts, then [group][512] last positions
+  __shared__ HueLutEntry s_lutHue[256];
   __shared__ uint16_t s_lut43[256];
   __shared__ uint16_t s_lut255[256];
   __shared__ unsigned long long s_best[32];
@@ -47,6 +59,7 @@ om_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParam
   if (cellRow >= M || N <= 0)
     return;                                               // uniform per CTA
   fill_div_luts(s_lut43, s_lut255);
+  fill_hue_lut(s_lutHue);
 
   const int W = g.width, H = g.height;
   const int ws = W / N, hs = H / M;                       // m_widthStep, m_heightStep (:587-588); remainders ignored
@@ -88,7 +101,7 @@ om_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParam
         {
           const uint32_t yy = __byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140);
           uint32_t hsv[2];
-          hsv_pair(yy, Cw[k >> 1], (k & 1) ? coef_planar1() : coef_planar0(), s_lut43, s_lut255, hsv[0], hsv[1]);
+          hsv_pair(yy, Cw[k >> 1], (k & 1) ? coef_planar1() : coef_planar0(), s_lutHue, s_lut255, hsv[0], hsv[1]);
 #pragma unroll
           for (int e = 0; e < 2; ++e)
           {
@@ -174,8 +187,7 @@ cudaError_t launch_om(const Geometry& g, int numFrames, const uint8_t* frames, c
   const int cpr = g.width / 16;
   if (cpr <= 0 || cpr > 1024)
     return cudaErrorInvalidValue;
-  int k = (256 + cpr - 1) / cpr;
-  if (cpr * k > 1024) k = 1024 / cpr;
+  const int k = rows_per_iteration(cpr, 192);
   const int threads = cpr * k;
   const int group = maxGridCols < OM_MAX_GROUP ? maxGridCols : OM_MAX_GROUP;
   const size_t smem = (size_t)2 * group * OM_BINS * sizeof(uint32_t);
@@ -196,14 +208,17 @@ __global__ void __launch_bounds__(1024)
 oo_bitmap_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
                  const int paramStride, uint16_t* __restrict__ bitmaps, const int cpr, const int rpi)
 {
+  __shared__ HueLutEntry s_lutHue[256];
   __shared__ uint16_t s_lut43[256];
   __shared__ uint16_t s_lut255[256];
   fill_div_luts(s_lut43, s_lut255);
+  fill_hue_lut(s_lutHue);
   __syncthreads();
 
   const int slabs = gridDim.y;
   const int frame = blockIdx.x;
   const FrameParams p = params[(size_t)frame * paramStride];
+  const HsvBounds bd = make_bounds(p.from, p.to);
   const int t = threadIdx.x;
   const int cc = t % cpr, rr = t / cpr;
   const int bw = g.width / 4, bh = g.height / 4;
@@ -229,7 +244,7 @@ oo_bitmap_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fra
       {
         const uint32_t yy = __byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140);
         const uint32_t det = detect_pair_bits(yy, Cw[k >> 1], (k & 1) ? coef_planar1() : coef_planar0(),
-                                              s_lut43, s_lut255, p.from, p.to, p.expected);
+                                              s_lutHue, s_lut255, bd, p.expected);
         meta[k >> 1] |= det << (r * 4 + (k & 1) * 2);
       }
     }
@@ -441,57 +456,116 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
   }
   __syncwarp();
 
+  // Raster replay, 32 metapixels per step.  Along a run of consecutive "on" cells the label is the running
+  // minimum of the non-zero labels seen so far (the left neighbour carries it), so it comes out of a
+  // segmented prefix-min scan over the lanes; a run that starts with no labelled neighbour opens a new
+  // label (numbered in raster order by a ballot rank).  The masses are order independent and are added
+  // per distinct label.  Only the cells where two DIFFERENT labels meet touch the equivalence table, and
+  // those are replayed one by one, in order, exactly as the reference does (:92-102).
+  const unsigned FULL = 0xFFFFFFFFu;
   for (int row = 0; row < bh; ++row)
   {
     for (int base = 0; base < bw; base += 32)
     {
       const int col = base + lane;
-      bool on = false;
-      if (col < bw)
+      const bool inside = col < bw;
+      const bool on = inside && __popc((unsigned)bm[row * bw + col]) > 2;   // pop(...) > METAPIX_SIZE/2 (:192)
+      // up-left, up, up-right labels (:69-83)
+      uint32_t p0 = 0, p1 = 0, p2 = 0;
+      if (on && row != 0)
       {
-        on = __popc((unsigned)bm[row * bw + col]) > 2;    // pop(...) > METAPIX_SIZE/2 (:192)
-        cur[col] = 0;
+        p1 = prev[col];
+        if (col != 0) p0 = prev[col - 1];
+        if (col != bw - 1) p2 = prev[col + 1];
       }
-      unsigned mask = __ballot_sync(0xFFFFFFFFu, on);
-      __syncwarp();
-      if (lane == 0)
+      const uint32_t carry = (base != 0) ? (uint32_t)cur[base - 1] : 0u;     // label of the cell left of this group
+      const unsigned onMask = __ballot_sync(FULL, on);
+      if (onMask == 0u)                                                      // nothing detected in these 32 cells
       {
-        while (mask)
+        if (inside) cur[col] = 0;
+        __syncwarp();
+        continue;
+      }
+      const bool leftOn = lane == 0 ? (carry != 0u) : ((onMask >> (lane - 1)) & 1u);
+      uint32_t mu = p0;                                                      // smallest non-zero up label
+      if (p1 && (p1 < mu || mu == 0)) mu = p1;
+      if (p2 && (p2 < mu || mu == 0)) mu = p2;
+      // a run start without any labelled neighbour opens a new label, numbered in raster order
+      const bool opens = on && !leftOn && mu == 0u;
+      const unsigned openMask = __ballot_sync(FULL, opens);
+      uint32_t x = on ? mu : 0u;
+      if (opens)
+      {
+        const int rank = __popc(openMask & ((1u << lane) - 1u));
+        const int lab = ncl + rank;
+        x = lab < maxLabels ? (uint32_t)lab : 0u;
+        if (lab < maxLabels)
         {
-          const int c = base + __ffs((int)mask) - 1;
-          mask &= mask - 1;
-          uint16_t a[4] = {0, 0, 0, 0};                   // left, up-left, up, up-right (:69-83)
-          if (row != 0)
-          {
-            a[2] = prev[c];
-            if (c != 0) a[1] = prev[c - 1];
-            if (c != bw - 1) a[3] = prev[c + 1];
-          }
-          if (c != 0) a[0] = cur[c - 1];
-          uint16_t v = a[0];                              // min(): smallest non-zero (:44-52)
+          eq[lab] = (uint16_t)lab;                                           // zero mass, not counted (:104-111)
+          cl[lab] = OoCluster{0, 0, 0};
+        }
+      }
+      ncl = min(ncl + __popc(openMask), maxLabels);
+      if (lane == 0 && on && carry != 0u)                                    // the run continues from the previous group
+        x = (x == 0u || carry < x) ? carry : x;
+      // segmented inclusive scan of "min over non-zero" along the runs
+      bool flag = !on || !leftOn || lane == 0;
 #pragma unroll
-          for (int n = 1; n < 4; ++n)
-            if ((a[n] < v && a[n] != 0) || v == 0)
-              v = a[n];
-          uint16_t lab = 0;
-          if (v)
-          {
-            lab = v;
-            cl[v].x += c; cl[v].y += row; cl[v].size += 1;
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t y = __shfl_up_sync(FULL, x, d);
+        const bool g2 = __shfl_up_sync(FULL, (int)flag, d) != 0;
+        if (lane >= d && !flag)
+        {
+          if (y != 0u && (x == 0u || y < x)) x = y;
+          flag = g2;
+        }
+      }
+      const uint32_t v = on ? x : 0u;
+      if (inside)
+        cur[col] = (uint16_t)v;
+      // left label of every cell: a[0] of the reference
+      uint32_t L = __shfl_up_sync(FULL, v, 1);
+      if (lane == 0) L = carry;
+      if (!on) L = 0u;
+      // masses: every on cell except the openers adds (col, row, 1) to its label
+      bool needAdd = on && !opens && v != 0u;
+      unsigned addMask = __ballot_sync(FULL, needAdd);
+      while (addMask)
+      {
+        const int leader = __ffs((int)addMask) - 1;
+        const uint32_t lab = __shfl_sync(FULL, v, leader);
+        const bool mine = needAdd && v == lab;
+        const unsigned mm = __ballot_sync(FULL, mine);
+        const int sumc = __reduce_add_sync(FULL, mine ? col : 0);
+        if (lane == leader)
+        {
+          const int cnt = __popc(mm);
+          cl[lab].x += sumc; cl[lab].y += row * cnt; cl[lab].size += cnt;
+        }
+        needAdd = needAdd && !mine;
+        addMask &= ~mm;
+      }
+      // equivalences: only where a different non-zero label touches the cell, replayed in raster order
+      const bool meets = on && !opens && v != 0u &&
+                         ((L && L != v) || (p0 && p0 != v) || (p1 && p1 != v) || (p2 && p2 != v));
+      unsigned meetMask = __ballot_sync(FULL, meets);
+      __syncwarp();
+      while (meetMask)
+      {
+        const int src = __ffs((int)meetMask) - 1;
+        meetMask &= meetMask - 1;
+        const uint32_t a0 = __shfl_sync(FULL, L, src), a1 = __shfl_sync(FULL, p0, src);
+        const uint32_t a2 = __shfl_sync(FULL, p1, src), a3 = __shfl_sync(FULL, p2, src);
+        const uint32_t vv = __shfl_sync(FULL, v, src);
+        if (lane == 0)
+        {
+          const uint32_t a[4] = {a0, a1, a2, a3};
 #pragma unroll
-            for (int n = 0; n < 4; ++n)
-              if (a[n])
-                if (!(a[n] == v || eq[a[n]] == eq[v]))
-                  eq[a[n]] = eq[v];
-          }
-          else if (ncl < maxLabels)
-          {
-            lab = (uint16_t)ncl;                          // a new label starts with ZERO mass (:104-111)
-            eq[ncl] = (uint16_t)ncl;
-            cl[ncl] = OoCluster{0, 0, 0};
-            ++ncl;
-          }
-          cur[c] = lab;
+          for (int n = 0; n < 4; ++n)
+            if (a[n])
+              if (!(a[n] == vv || eq[a[n]] == eq[vv]))
+                eq[a[n]] = eq[vv];
         }
       }
       __syncwarp();
@@ -557,8 +631,7 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
   const int cpr = g.width / 16;
   if (cpr <= 0 || cpr > 1024)
     return cudaErrorInvalidValue;
-  int k = (256 + cpr - 1) / cpr;
-  if (cpr * k > 1024) k = 1024 / cpr;
+  const int k = rows_per_iteration(cpr, 192);
   const int bh = g.height / 4;
   int slabs = (148 * 8 + numFrames - 1) / numFrames;
   const int maxSlabs = bh / (k * 2) > 0 ? bh / (k * 2) : 1;

@@ -116,68 +116,138 @@ __device__ __forceinline__ bool detect_hsv(uint32_t hsv, uint32_t from, uint32_t
   return mask == expected;
 }
 
+// ---- packed HSV of a pixel pair ----------------------------------------------------------------
+// Everything that can stays in two 16-bit lanes, and the 8-bit channels are kept SCALED BY 64 with their
+// low six bits cleared (c6 = clamp(value, 0, 16383) & ~63 == channel << 6): that drops the per-channel
+// shift, and all derived quantities stay exact integers --
+//   V6 = max6,  d6 = max6 - min6,  S = (lut255[V] * d6) >> 14,  H = ((off * 64 + lut43[d] * diff6) >> 14) & 255.
+// The hue LUT entry carries {t, -16384 * t} so that the +16384 bias which keeps the packed channel
+// differences positive (one IADD3 each, no lane borrow) costs nothing to remove.
+struct HueLutEntry { int32_t t; int32_t tBias; };            // lut43[d], -16384 * lut43[d]
+
+__device__ __forceinline__ void fill_hue_lut(HueLutEntry* lut)
+{
+  for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x)
+  {
+    const int32_t t = i ? (int32_t)(11008u / i) : 0;
+    lut[i].t = t;
+    lut[i].tBias = -16384 * t;
+  }
+}
+
+// 64-scaled channel lanes from key lanes: clamp to [0, 16383] in the value domain, clear bias and low 6 bits
+__device__ __forceinline__ uint32_t chan6_from_key(uint32_t k)
+{
+  return __vminu2(__vmaxu2(k, 0x80008000u), 0xBFFFBFFFu) & 0x3FC03FC0u;
+}
+
+// sx (S = (sx >> 14) & 255) of both pixels from the packed max6 / d6 lanes
+__device__ __forceinline__ void sat_scaled(uint32_t mx6, uint32_t d6, const uint16_t* __restrict__ lut255,
+                                           uint32_t& sx0, uint32_t& sx1)
+{
+  const uint16_t* base = lut255;
+  const uint32_t t0 = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(base) + ((mx6 & 0xFFFFu) >> 5));
+  const uint32_t t1 = *reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(base) + (mx6 >> 21));
+  sx0 = t0 * (d6 & 0xFFFFu);
+  sx1 = t1 * (d6 >> 16);
+}
+
+// hx (H = (hx >> 14) & 255) of both pixels.  Sector choice as the reference's _cmpeq2 (:230-242):
+// max == G -> green (off 21845, B - R); else max == B -> blue (43690, R - G); else red (0, G - B).
+__device__ __forceinline__ void hue_scaled(uint32_t r6, uint32_t g6, uint32_t b6, uint32_t mx6, uint32_t d6,
+                                           const HueLutEntry* __restrict__ lutHue, int32_t& hx0, int32_t& hx1)
+{
+  // lane masks 0xFFFF where max != G / max != B
+  const uint32_t notG = __vminu2(mx6 ^ g6, 0x00010001u) * 0xFFFFu;
+  const uint32_t notB = __vminu2(mx6 ^ b6, 0x00010001u) * 0xFFFFu;
+  // biased differences, lanes in [64, 32704]
+  const uint32_t dG = b6 + 0x40004000u - r6;
+  const uint32_t dB = r6 + 0x40004000u - g6;
+  const uint32_t dR = g6 + 0x40004000u - b6;
+  const uint32_t dsel = (~notG & dG) | (notG & ((~notB & dB) | (notB & dR)));
+  const uint32_t osel = (~notG & 0x55555555u) | (notG & ~notB & 0xAAAAAAAAu);       // 21845 / 43690 / 0 per lane
+  const HueLutEntry e0 = *reinterpret_cast<const HueLutEntry*>(reinterpret_cast<const uint8_t*>(lutHue) + ((d6 & 0xFFFFu) >> 3));
+  const HueLutEntry e1 = *reinterpret_cast<const HueLutEntry*>(reinterpret_cast<const uint8_t*>(lutHue) + (d6 >> 19));
+  hx0 = e0.t * (int32_t)(dsel & 0xFFFFu) + ((int32_t)(osel & 0xFFFFu) * 64 + e0.tBias);
+  hx1 = e1.t * (int32_t)(dsel >> 16) + ((int32_t)(osel >> 16) * 64 + e1.tBias);
+}
+
 // HSV (0x00VVSSHH) of both pixels of a pair.
 __device__ __forceinline__ void hsv_pair(uint32_t yy, uint32_t cw, const ChromaCoef coef,
-                                         const uint16_t* __restrict__ lut43, const uint16_t* __restrict__ lut255,
+                                         const HueLutEntry* __restrict__ lutHue, const uint16_t* __restrict__ lut255,
                                          uint32_t& hsv0, uint32_t& hsv1)
 {
   uint32_t kr, kg, kb;
   rgb_keys(yy, cw, coef, kr, kg, kb);
-  const uint32_t r2 = chan8_from_key(kr), g2 = chan8_from_key(kg), b2 = chan8_from_key(kb);
-  hsv0 = hsv_from_rgb8((int32_t)(r2 & 0xFFFFu), (int32_t)(g2 & 0xFFFFu), (int32_t)(b2 & 0xFFFFu), lut43, lut255);
-  hsv1 = hsv_from_rgb8((int32_t)(r2 >> 16), (int32_t)(g2 >> 16), (int32_t)(b2 >> 16), lut43, lut255);
+  const uint32_t r6 = chan6_from_key(kr), g6 = chan6_from_key(kg), b6 = chan6_from_key(kb);
+  const uint32_t mx6 = __vimax3_u16x2(r6, g6, b6), mn6 = __vimin3_u16x2(r6, g6, b6);
+  const uint32_t d6 = mx6 - mn6;
+  uint32_t sx0, sx1;
+  int32_t hx0, hx1;
+  sat_scaled(mx6, d6, lut255, sx0, sx1);
+  hue_scaled(r6, g6, b6, mx6, d6, lutHue, hx0, hx1);
+  hsv0 = ((mx6 & 0xFFFFu) << 10) | ((sx0 >> 6) & 0xFF00u) | (((uint32_t)hx0 >> 14) & 0xFFu);
+  hsv1 = ((mx6 >> 16) << 10) | ((sx1 >> 6) & 0xFF00u) | (((uint32_t)hx1 >> 14) & 0xFFu);
 }
 
 // ---- threshold of a pixel pair with warp-level early out --------------------------------------
 // det = ((hsv <u4 from) | (hsv >u4 to)) == expected with expected in {0,1}: S and V must always be inside
 // their bounds, only the hue test can be inverted.  So V (a max3 on the keys) and S (one LUT fetch per
-// pixel) are tested first, and the expensive hue (three channel clamps, sector select, second LUT) is
-// only computed when some lane of the warp still has a candidate -- on frames where the wanted colour is
-// a small part of the picture most warps stop after the cheap tests.  Bit 0 / bit 1 = pixel 0 / 1.
+// pixel) are tested first, and the expensive hue is only computed when some lane of the warp still has a
+// candidate -- on frames where the wanted colour is a small part of the picture most warps stop after the
+// cheap tests.  All comparisons are made on the scaled forms (no shifts to bytes).  Bit 0 / 1 = pixel 0 / 1.
+struct HsvBounds {                     // loop-invariant, derived once per thread from FrameParams.from/to
+  uint32_t vAdd2, vSub2;               // guard-bit constants for the packed V test on 64-scaled lanes
+  uint32_t sLo, sSpan;                 // sx - sLo <=u sSpan
+  uint32_t hLo, hSpan;                 // ((hx - hLo) & 0x3FFFFF) <=u hSpan
+  uint32_t hValid;                     // hue interval non-empty
+};
+
+__device__ __forceinline__ HsvBounds make_bounds(uint32_t from, uint32_t to)
+{
+  HsvBounds b;
+  const uint32_t hf = from & 0xFFu, ht = to & 0xFFu, sf = (from >> 8) & 0xFFu, st = (to >> 8) & 0xFFu;
+  const uint32_t vf = (from >> 16) & 0xFFu, vt = (to >> 16) & 0xFFu;
+  // x6 >= vf*64  <=> bit 15 of (x6 + 0x8000 - vf*64);  x6 > vt*64 <=> bit 15 of (x6 + 0x7FFF - vt*64)
+  b.vAdd2 = (0x8000u - vf * 64u) * 0x10001u;
+  b.vSub2 = (0x7FFFu - vt * 64u) * 0x10001u;
+  b.sLo = sf << 14;
+  b.sSpan = st >= sf ? (((st - sf + 1u) << 14) - 1u) : 0u;
+  if (st < sf) b.sLo = 0xFFFFFFFFu;                    // sx < 2^30, so sx - sLo wraps above any span: never inside
+  b.hLo = hf << 14;
+  b.hSpan = ht >= hf ? (((ht - hf + 1u) << 14) - 1u) : 0u;
+  b.hValid = ht >= hf ? 1u : 0u;
+  return b;
+}
+
 __device__ __forceinline__ uint32_t detect_pair_bits(uint32_t yy, uint32_t cw, const ChromaCoef coef,
-                                                     const uint16_t* __restrict__ lut43,
+                                                     const HueLutEntry* __restrict__ lutHue,
                                                      const uint16_t* __restrict__ lut255,
-                                                     uint32_t from, uint32_t to, uint32_t expected)
+                                                     const HsvBounds& bd, uint32_t expected)
 {
   uint32_t kr, kg, kb;
   rgb_keys(yy, cw, coef, kr, kg, kb);
-  const uint32_t mx2 = chan8_from_key(__vimax3_u16x2(kr, kg, kb));     // V of both pixels, 0x00VV00VV
-  const uint32_t vf = (from >> 16) & 0xFFu, vt = (to >> 16) & 0xFFu;
-  // 8-bit values in 16-bit lanes leave room for a guard bit: bit 15 of (x + 0x8000 - lo) <=> x >= lo
-  const uint32_t vIn = (mx2 + (0x8000u - vf) * 0x10001u) & ~(mx2 + (0x7FFFu - vt) * 0x10001u) & 0x80008000u;
+  const uint32_t mx6 = chan6_from_key(__vimax3_u16x2(kr, kg, kb));     // V*64 of both pixels
+  const uint32_t vIn = (mx6 + bd.vAdd2) & ~(mx6 + bd.vSub2) & 0x80008000u;
   const unsigned am = __activemask();
   if (!__any_sync(am, vIn != 0u))
     return 0u;
-  const uint32_t mn2 = chan8_from_key(__vimin3_u16x2(kr, kg, kb));
-  const uint32_t d2 = mx2 - mn2;                                       // lanes >= 0, no borrow
-  const uint32_t sf = (from >> 8) & 0xFFu, st = (to >> 8) & 0xFFu;
-  const uint32_t s0 = (((uint32_t)lut255[mx2 & 0xFFFFu] * (d2 & 0xFFFFu)) >> 8) & 0xFFu;
-  const uint32_t s1 = (((uint32_t)lut255[mx2 >> 16] * (d2 >> 16)) >> 8) & 0xFFu;
+  const uint32_t mn6 = chan6_from_key(__vimin3_u16x2(kr, kg, kb));
+  const uint32_t d6 = mx6 - mn6;                                       // lanes >= 0, no borrow
+  uint32_t sx0, sx1;
+  sat_scaled(mx6, d6, lut255, sx0, sx1);
   uint32_t cand = 0u;
-  if ((vIn & 0x8000u) && s0 >= sf && s0 <= st) cand |= 1u;
-  if ((vIn & 0x80000000u) && s1 >= sf && s1 <= st) cand |= 2u;
+  if ((vIn & 0x8000u) && (sx0 - bd.sLo) <= bd.sSpan) cand |= 1u;
+  if ((vIn & 0x80000000u) && (sx1 - bd.sLo) <= bd.sSpan) cand |= 2u;
   if (!__any_sync(am, cand != 0u))
     return 0u;
-  // hue: (off + lut43[d] * diff) >> 8 & 255 with the sector chosen as the reference's _cmpeq2 does
-  const uint32_t r2 = chan8_from_key(kr), g2 = chan8_from_key(kg), b2 = chan8_from_key(kb);
-  const uint32_t hf = from & 0xFFu, ht = to & 0xFFu;
-  uint32_t det = 0u;
-#pragma unroll
-  for (int e = 0; e < 2; ++e)
-  {
-    const int32_t r = (int32_t)(e ? r2 >> 16 : r2 & 0xFFFFu), g = (int32_t)(e ? g2 >> 16 : g2 & 0xFFFFu);
-    const int32_t b = (int32_t)(e ? b2 >> 16 : b2 & 0xFFFFu);
-    const int32_t mx = (int32_t)(e ? mx2 >> 16 : mx2 & 0xFFFFu), d = (int32_t)(e ? d2 >> 16 : d2 & 0xFFFFu);
-    int32_t off, diff;
-    if (mx == g)      { off = 21845; diff = b - r; }
-    else if (mx == b) { off = 43690; diff = r - g; }
-    else              { off = 0;     diff = g - b; }
-    const uint32_t h = (((uint32_t)(off + (int32_t)lut43[d] * diff)) >> 8) & 0xFFu;
-    const uint32_t hout = (h < hf || h > ht) ? 1u : 0u;
-    if ((cand >> e) & 1u)
-      det |= (hout == expected ? 1u : 0u) << e;
-  }
-  return det;
+  const uint32_t r6 = chan6_from_key(kr), g6 = chan6_from_key(kg), b6 = chan6_from_key(kb);
+  int32_t hx0, hx1;
+  hue_scaled(r6, g6, b6, mx6, d6, lutHue, hx0, hx1);
+  const uint32_t in0 = (bd.hValid && (((uint32_t)hx0 - bd.hLo) & 0x3FFFFFu) <= bd.hSpan) ? 1u : 0u;
+  const uint32_t in1 = (bd.hValid && (((uint32_t)hx1 - bd.hLo) & 0x3FFFFFu) <= bd.hSpan) ? 1u : 0u;
+  // hout == expected: expected 0 -> hue inside, expected 1 -> hue outside
+  return cand & (((in0 ^ expected) & 1u) | (((in1 ^ expected) & 1u) << 1));
 }
 
 // ---- 128-bit streaming load ------------------------------------------------------------------
