@@ -255,6 +255,10 @@ void trikb200_setSlabsPerFrame(XDAS_Int32 slabs);
 void trikb200_setLoadStages(XDAS_Int32 stages);
 /* tuning knob: target CTA size of the sum kernels (rounded to a whole number of rows per iteration), 0 = default */
 void trikb200_setBlockThreads(XDAS_Int32 threads);
+/* tuning knob: 1 (default) launches the line kernel with programmatic stream serialisation, so the next batch's
+ * CTAs are placed while the previous batch drains (each kernel still waits for all earlier work of the stream
+ * before its first memory access); 0 = plain launches */
+void trikb200_setOverlapLaunch(XDAS_Int32 on);
 /* last CUDA / argument error message of this thread ("" if none) */
 const char* trikb200_lastError(void);
 

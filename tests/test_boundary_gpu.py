@@ -29,7 +29,9 @@ def both(kind, params=None):
 
 
 def frame_for(kind, w=320, h=240):
-    return synth.make_frame("scene", 3, w, h, sensors.layout_of(xdm.KIND_OF[kind]))
+    # OO: a frame with >= 8 labels -- with fewer the reference reads past its cluster vector (undefined, can SIGFPE)
+    fam, seed = ("blobs", 1) if kind == "oo" else ("scene", 3)
+    return synth.make_frame(fam, seed, w, h, sensors.layout_of(xdm.KIND_OF[kind]))
 
 
 def default_in_alg(kind):

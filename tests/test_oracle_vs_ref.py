@@ -74,9 +74,13 @@ def test_sensor_frames(kind, size):
             fr = ref.aligned_bytes(f0.size)
             fr[:] = f0
             seed = 77 + call
-            ret, out, _ = rs.process(fr, ref.IN_ARGS[kind](*args), seed=seed)
             ok, oout = orc.process(fr, ref.IN_ARGS[kind](*args), seed=seed)
-            assert ret == 0 and ok == 1
+            assert ok == 1
+            if orc.last_flags() and kind == "oo":
+                continue                                   # fewer than 8 labels: the reference reads past its vector
+                                                           # (garbage sizes, sometimes SIGFPE) -- never run it there
+            ret, out, _ = rs.process(fr, ref.IN_ARGS[kind](*args), seed=seed)
+            assert ret == 0
             if orc.last_flags():
                 continue                                   # undefined behaviour of the reference, see trik_oracle.h
             a, b = ref.struct_bytes(out), ref.struct_bytes(oout)
@@ -100,11 +104,12 @@ def test_object_sensor_sort_ties():
         fr = ref.aligned_bytes(f0.size)
         fr[:] = f0
         for args in [(1, 120, 25 + seed, 60, 35, 55, 40, 0), (1, 30 * seed, 20, 50, 30, 50, 45, 0)]:
-            ret, out, _ = rs.process(fr, ref.ObjInArgs(*args))
             ok, oout = orc.process(fr, ref.ObjInArgs(*args))
-            assert ret == 0 and ok == 1
+            assert ok == 1
             if orc.last_flags():
-                continue
+                continue                                   # see test_sensor_frames: the reference is not run here
+            ret, out, _ = rs.process(fr, ref.ObjInArgs(*args))
+            assert ret == 0
             assert ref.struct_bytes(out) == ref.struct_bytes(oout), (seed, args)
             nontrivial += 1
     assert nontrivial >= 12

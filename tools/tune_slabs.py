@@ -30,6 +30,7 @@ ia = xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 40, 0)
 SLABS = [int(x) for x in os.environ.get("SLABS", "0").split(",")]
 STAGES = [int(x) for x in os.environ.get("STAGES", "-1,100,102,104,200,202,204").split(",")]
 THREADS = [int(x) for x in os.environ.get("THREADS", "0").split(",")]
+lib().trikb200_setOverlapLaunch(int(os.environ.get("OVERLAP", "1")))
 ref_out = None
 for stages, slabs, threads in [(a, b, c) for a in STAGES for b in SLABS for c in THREADS]:
     lib().trikb200_setBlockThreads(threads)
@@ -56,5 +57,5 @@ for stages, slabs, threads in [(a, b, c) for a in STAGES for b in SLABS for c in
     if ref_out is None:
         ref_out = cur
     assert cur == ref_out, "results changed with the tuning knobs"
-    print(json.dumps({"sensor": kind, "size": "%dx%d" % (w, h), "batch": n, "slabs": slabs, "stages": stages, "threads": threads, "ms": best,
+    print(json.dumps({"sensor": kind, "size": "%dx%d" % (w, h), "batch": n, "slabs": slabs, "stages": stages, "threads": threads, "overlap": int(os.environ.get("OVERLAP", "1")), "ms": best,
                       "GBps": n * w * h * 2 / best / 1e6}), flush=True)

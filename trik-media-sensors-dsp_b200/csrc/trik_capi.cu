@@ -131,6 +131,10 @@ struct Instance {
   uint8_t*     dPreview = nullptr;  size_t dPreviewCap = 0;
   // pinned host staging
   FrameParams* hParams = nullptr;   size_t hParamsCap = 0;
+  cudaEvent_t  hParamsFree = nullptr;                          // completes when the last upload has read hParams
+  std::vector<FrameParams> paramsScratch;                      // a batch's parameters before they are staged
+  // the single broadcast record dParams[0] currently holds, and the stream that uploaded it
+  FrameParams  dBroadcast = {};     bool dBroadcastValid = false;  cudaStream_t dBroadcastStream = nullptr;
   uint8_t*     hOut = nullptr;      size_t hOutCap = 0;
   int*         hFlagged = nullptr;  size_t hFlaggedCap = 0;
   int32_t*     hHist = nullptr;     size_t hHistCap = 0;
@@ -156,6 +160,8 @@ struct Instance {
     cudaFree(dFlagged);  dFlagged = nullptr;  dFlaggedCap = 0;
     cudaFree(dHist);     dHist = nullptr;     dHistCap = 0;
     cudaFreeHost(hParams);  hParams = nullptr;  hParamsCap = 0;
+    if (hParamsFree) { cudaEventDestroy(hParamsFree); hParamsFree = nullptr; }
+    dBroadcastValid = false;
     cudaFreeHost(hOut);     hOut = nullptr;     hOutCap = 0;
     cudaFreeHost(hFlagged); hFlagged = nullptr; hFlaggedCap = 0;
     cudaFreeHost(hHist);    hHist = nullptr;    hHistCap = 0;
@@ -441,11 +447,35 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
   if (b.streamIds && (int)in->streamStates.size() < b.numStreams)
     in->streamStates.resize((size_t)b.numStreams);
   const size_t np = broadcast ? 1 : (size_t)b.n;
-  if (!in->grow_pinned(in->hParams, in->hParamsCap, np)) return false;
+  const FrameParams* const dParamsBefore = in->dParams;
   if (!in->grow_device(in->dParams, in->dParamsCap, np, false)) return false;
+  if (in->dParams != dParamsBefore)
+    in->dBroadcastValid = false;
+  in->paramsScratch.assign(np, FrameParams{});
   for (size_t i = 0; i < np; ++i)
-    prepare_frame_params(kind, in->geo, b.in_args((int)i), b.streamIds ? in->streamStates[(size_t)b.streamIds[i]] : in->state, in->hParams[i]);
-  CUDA_TRY(cudaMemcpyAsync(in->dParams, in->hParams, np * sizeof(FrameParams), cudaMemcpyHostToDevice, s));
+    prepare_frame_params(kind, in->geo, b.in_args((int)i), b.streamIds ? in->streamStates[(size_t)b.streamIds[i]] : in->state, in->paramsScratch[i]);
+  // A broadcast record that dParams[0] already holds (uploaded on this stream) is not sent again, so
+  // back-to-back batches with unchanged arguments are kernel launches only.  Otherwise stage through
+  // pinned memory; an asynchronous upload may still be reading it, hence the event.
+  const bool resident = broadcast && in->dBroadcastValid && in->dBroadcastStream == s
+                        && std::memcmp(&in->dBroadcast, &in->paramsScratch[0], sizeof(FrameParams)) == 0;
+  if (!resident)
+  {
+    if (in->hParamsFree)
+      CUDA_TRY(cudaEventSynchronize(in->hParamsFree));
+    else
+      CUDA_TRY(cudaEventCreateWithFlags(&in->hParamsFree, cudaEventDisableTiming));
+    if (!in->grow_pinned(in->hParams, in->hParamsCap, np)) return false;
+    std::memcpy(in->hParams, in->paramsScratch.data(), np * sizeof(FrameParams));
+    CUDA_TRY(cudaMemcpyAsync(in->dParams, in->hParams, np * sizeof(FrameParams), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(in->hParamsFree, s));
+    in->dBroadcastValid = broadcast;
+    if (broadcast)
+    {
+      in->dBroadcast = in->paramsScratch[0];
+      in->dBroadcastStream = s;
+    }
+  }
 
   // 2. frames
   Geometry g = in->geo;
@@ -1274,6 +1304,7 @@ int64_t trikb200_launchCount(void) { return launch_count(); }
 void trikb200_setSlabsPerFrame(XDAS_Int32 slabs) { g_slabsPerFrame = slabs; }
 void trikb200_setLoadStages(XDAS_Int32 stages) { set_sum_stages(stages); }
 void trikb200_setBlockThreads(XDAS_Int32 threads) { set_target_threads(threads); }
+void trikb200_setOverlapLaunch(XDAS_Int32 on) { set_overlap_launch(on); }
 const char* trikb200_lastError(void) { return t_lastError.c_str(); }
 
 /* test probes: exhaustive pixel functions straight from the device code (tests/test_pixel_gpu.py) */

@@ -26,6 +26,8 @@ static long long g_launches = 0;
 //   v / 100 = 0 per-sensor default kernel, 1 force the first-version kernel, 2 force the tuned line kernel.
 static int g_targetThreads = 0;             // 0 = default (about 256 threads per CTA)
 void set_target_threads(int t) { g_targetThreads = t; }
+static int g_overlapLaunch = 1;              // programmatic dependent launch of the tuned line kernel
+void set_overlap_launch(int on) { g_overlapLaunch = on ? 1 : 0; }
 static int g_tuneStages = -1;
 static int g_tuneKernel = 0;
 static bool g_legacyLineKernel = false;      // resolved per launch
@@ -449,11 +451,16 @@ vsum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePar
   __shared__ uint32_t s_red[32][4];
   extern __shared__ uint4 s_ring[];
 
+  // Programmatic dependent launch: let the next kernel of the stream start placing its CTAs while this
+  // grid drains, and (as such a successor) wait for everything before us in the stream to be complete
+  // and visible before the first global access -- stream order as the caller sees it is unchanged.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int frame = blockIdx.x / slabs;
   const int slab  = blockIdx.x - frame * slabs;
   const int t  = threadIdx.x;
   const int cc = t % cpr;
   const int rr = t / cpr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const FrameParams p = params[(size_t)frame * paramStride];
 
   const int r0 = slab * rowsPerSlab;
@@ -718,8 +725,15 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
   do {                                                                                                           \
     if (ringBytes > 48 * 1024)                                                                                   \
       cudaFuncSetAttribute(vsum_kernel<PL, ST, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);\
-    vsum_kernel<PL, ST, MT><<<(unsigned)grid, threads, ringBytes, stream>>>(g, frames, params, paramStride, acc, \
-                                                                            out, slabs, rowsPerSlab, cpr, rpi);  \
+    cudaLaunchConfig_t cfg = {};                                                                                 \
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads);                                  \
+    cfg.dynamicSmemBytes = ringBytes; cfg.stream = stream;                                                       \
+    cudaLaunchAttribute attr[1];                                                                                 \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                             \
+    attr[0].val.programmaticStreamSerializationAllowed = 1;                                                      \
+    cfg.attrs = attr; cfg.numAttrs = g_overlapLaunch ? 1u : 0u;                                                  \
+    cudaLaunchKernelEx(&cfg, vsum_kernel<PL, ST, MT>, g, frames, params, paramStride, acc, out, slabs,           \
+                       rowsPerSlab, cpr, rpi);                                                                   \
   } while (0)
 #define TRIK_LAUNCH_V(PL, ST)                                   \
   do { if (threads <= 512) TRIK_LAUNCH_V2(PL, ST, 512); else TRIK_LAUNCH_V2(PL, ST, 1024); } while (0)
@@ -729,6 +743,8 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
     case 0: TRIK_LAUNCH_V(PL, 0); break;                        \
     case 2: TRIK_LAUNCH_V(PL, 2); break;                        \
     case 4: TRIK_LAUNCH_V(PL, 4); break;                        \
+    case 6: TRIK_LAUNCH_V(PL, 6); break;                        \
+    case 8: TRIK_LAUNCH_V(PL, 8); break;                        \
     default: return cudaErrorInvalidValue;                      \
   }
   switch (kind)

@@ -100,6 +100,7 @@ cudaError_t launch_probe_yuv2hsv(uint32_t first, uint32_t count, uint32_t* out, 
 int sum_sensor_block_threads(int kind, int width);
 void set_sum_stages(int stages);
 void set_target_threads(int threads);
+void set_overlap_launch(int on);
 long long launch_count();
 
 } // namespace trikb200
