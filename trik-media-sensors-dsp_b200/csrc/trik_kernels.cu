@@ -31,6 +31,7 @@ void set_overlap_launch(int on) { g_overlapLaunch = on ? 1 : 0; }
 static int g_tuneStages = -1;
 static int g_tuneKernel = 0;
 static bool g_legacyLineKernel = false;      // resolved per launch
+static bool g_widePlanarKernel = false;      // resolved per launch: OL through vsum16_kernel
 static int g_sumStages = 0;                  // resolved per launch
 void set_sum_stages(int v)
 {
@@ -41,7 +42,8 @@ void set_sum_stages(int v)
 static void resolve_tuning(int kind)
 {
   const bool tunedDefault = (kind == KIND_WL);
-  g_legacyLineKernel = g_tuneKernel == 1 ? true : (g_tuneKernel == 2 ? false : !tunedDefault);
+  g_legacyLineKernel = g_tuneKernel == 1 ? true : (g_tuneKernel == 2 || g_tuneKernel == 3 ? false : !tunedDefault);
+  g_widePlanarKernel = kind == KIND_OL && g_tuneKernel == 3;
   if (g_tuneStages >= 0)
     g_sumStages = g_tuneStages;
   else
@@ -651,7 +653,176 @@ vsum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePar
   }
 }
 
-static int sum_chunk_pixels(int kind) { return (kind == KIND_OL && g_legacyLineKernel) ? 16 : 8; }
+// ---------------------------------------------------------------------------------------------
+// YUV422P line sensor (OL), 16 pixels per thread and row: one 16-byte luma chunk and the 16 chroma
+// bytes under it, i.e. two full-width cp.async per ring slot and eight pixel pairs of vtest_lanes work
+// per iteration.  Same bookkeeping as vsum_kernel (per-position {N, N+1} lanes, window folded into
+// the caps, cross band as a difference of snapshots).
+// ---------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(512, 2)
+vsum16_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+              const int paramStride, SumAcc* __restrict__ acc, TargetOut* __restrict__ out,
+              const int slabs, const int rowsPerSlab, const int cpr, const int rpi)
+{
+  static_assert(STAGES >= 2, "ring depth");
+  __shared__ uint32_t s_red[32][4];
+  extern __shared__ uint4 s_ring[];            // [STAGES][2][blockDim]: luma chunk, chroma chunk
+
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int frame = blockIdx.x / slabs;
+  const int slab  = blockIdx.x - frame * slabs;
+  const int t  = threadIdx.x;
+  const int cc = t % cpr;
+  const int rr = t / cpr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const FrameParams p = params[(size_t)frame * paramStride];
+
+  const int r0 = slab * rowsPerSlab;
+  const int r1 = min(r0 + rowsPerSlab, g.height);
+  const int firstRow = r0 + rr;
+  const int iters = firstRow < r1 ? (r1 - firstRow + rpi - 1) / rpi : 0;
+  const uint8_t* fillPtr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)firstRow * g.lineLength;
+  const size_t rowStep = (size_t)rpi * g.lineLength;
+  const size_t chromaOfs = (size_t)g.height * g.lineLength;
+
+  const uint32_t negKlo2 = p.negKlo2, n2 = p.n2;
+  const uint32_t nLane = n2 & 0xFFFFu;
+  const uint32_t np1 = n2 + 0x00010001u;
+  // window columns 5..W-5: chunk 0 loses its pixels 0..4 (pairs 0, 1 and the even pixel of pair 2),
+  // the last chunk its pixels 12..15 (pairs 6, 7)
+  uint32_t cap01 = np1, cap2 = np1, cap67 = np1;
+  if (cc == 0)       { cap01 = n2; cap2 = (np1 & 0xFFFF0000u) | nLane; }
+  if (cc == cpr - 1) { cap67 = n2; }
+
+  int itA = 0, itB = 0;
+  if (p.hStart <= p.hStop)
+  {
+    const long long a = (long long)p.hStart - firstRow, b = (long long)p.hStop + 1 - firstRow;
+    itA = a <= 0 ? 0 : (int)min((long long)iters, (a + rpi - 1) / rpi);
+    itB = b <= 0 ? 0 : (int)min((long long)iters, (b + rpi - 1) / rpi);
+  }
+
+  uint32_t S0 = 0u, S1 = 0u, S2 = 0u, S3 = 0u, S4 = 0u, S5 = 0u, S6 = 0u, S7 = 0u;
+  uint32_t snapA = 0u, snapB = 0u;
+  const int nthreads = (int)blockDim.x;
+  uint4* const mySlot = s_ring + t;
+
+  int fillIt = 0;
+#pragma unroll
+  for (int sIdx = 0; sIdx < STAGES - 1; ++sIdx)
+  {
+    if (fillIt < iters)
+    {
+      cp_async16(mySlot + (sIdx * 2) * nthreads, fillPtr);
+      cp_async16(mySlot + (sIdx * 2 + 1) * nthreads, fillPtr + chromaOfs);
+    }
+    cp_async_commit();
+    ++fillIt;
+    fillPtr += rowStep;
+  }
+  // three runs of iterations -- before, inside and after the cross band -- with a snapshot of the
+  // accumulators between them, so the band costs nothing per iteration
+  int it = 0;
+#pragma unroll 1
+  for (int seg = 0; seg < 3; ++seg)
+  {
+    const int segEnd = seg == 0 ? itA : (seg == 1 ? itB : iters);
+#pragma unroll 1
+    for (; it < segEnd; ++it)
+    {
+      if (fillIt < iters)
+      {
+        const int fillSlot = (it + STAGES - 1) % STAGES;
+        cp_async16(mySlot + (fillSlot * 2) * nthreads, fillPtr);
+        cp_async16(mySlot + (fillSlot * 2 + 1) * nthreads, fillPtr + chromaOfs);
+      }
+      cp_async_commit();
+      ++fillIt;
+      fillPtr += rowStep;
+      cp_async_wait<STAGES - 1>();
+      const int slot = it % STAGES;
+      const uint4 L = mySlot[(slot * 2) * nthreads];
+      const uint4 Cw = mySlot[(slot * 2 + 1) * nthreads];
+      S0 = __vadd2(S0, vtest_planar<0>(L.x, Cw.x, negKlo2, n2, cap01));
+      S1 = __vadd2(S1, vtest_planar<1>(L.x, Cw.x, negKlo2, n2, cap01));
+      S2 = __vadd2(S2, vtest_planar<0>(L.y, Cw.y, negKlo2, n2, cap2));
+      S3 = __vadd2(S3, vtest_planar<1>(L.y, Cw.y, negKlo2, n2, np1));
+      S4 = __vadd2(S4, vtest_planar<0>(L.z, Cw.z, negKlo2, n2, np1));
+      S5 = __vadd2(S5, vtest_planar<1>(L.z, Cw.z, negKlo2, n2, np1));
+      S6 = __vadd2(S6, vtest_planar<0>(L.w, Cw.w, negKlo2, n2, cap67));
+      S7 = __vadd2(S7, vtest_planar<1>(L.w, Cw.w, negKlo2, n2, cap67));
+    }
+    if (seg < 2)
+    {
+      const uint32_t tot = __vadd2(__vadd2(__vadd2(S0, S1), __vadd2(S2, S3)), __vadd2(__vadd2(S4, S5), __vadd2(S6, S7)));
+      if (seg == 0) snapA = tot; else snapB = tot;
+    }
+  }
+
+  const uint32_t total = __vadd2(__vadd2(__vadd2(S0, S1), __vadd2(S2, S3)), __vadd2(__vadd2(S4, S5), __vadd2(S6, S7)));
+  (void)total;
+  const uint32_t passBias2 = (((uint32_t)iters * nLane) & 0xFFFFu) * 0x10001u;
+  const uint32_t f[8] = {lanes_sub(S0, passBias2), lanes_sub(S1, passBias2), lanes_sub(S2, passBias2), lanes_sub(S3, passBias2),
+                         lanes_sub(S4, passBias2), lanes_sub(S5, passBias2), lanes_sub(S6, passBias2), lanes_sub(S7, passBias2)};
+  uint32_t fails = 0u, inIdx = 0u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+  {
+    const uint32_t tk = lanes_total(f[k]);
+    fails += tk;
+    inIdx += 2u * (uint32_t)k * tk + (f[k] >> 16);       // in-chunk pixel index of pair k, lane e: 2k + e
+  }
+  uint32_t sxFail = fails * ((uint32_t)cc * 16u) + inIdx;
+  const uint32_t bandBias2 = (((uint32_t)(itB - itA) * 8u * nLane) & 0xFFFFu) * 0x10001u;
+  uint32_t crossFail = lanes_total(lanes_sub(lanes_sub(snapB, snapA), bandBias2));
+
+  __syncthreads();
+  const unsigned am = __activemask();
+  fails  = __reduce_add_sync(am, fails);
+  sxFail = __reduce_add_sync(am, sxFail);
+  crossFail = __reduce_add_sync(am, crossFail);
+  const int warp = t >> 5, lane = t & 31, nwarps = (blockDim.x + 31) >> 5;
+  if (lane == 0)
+  {
+    s_red[warp][0] = fails; s_red[warp][1] = sxFail; s_red[warp][3] = crossFail;
+  }
+  __syncthreads();
+  if (warp == 0)
+  {
+    uint32_t a = 0, b = 0, d = 0;
+    if (lane < nwarps) { a = s_red[lane][0]; b = s_red[lane][1]; d = s_red[lane][3]; }
+    const unsigned fm = __activemask();
+    a = __reduce_add_sync(fm, a);
+    b = __reduce_add_sync(fm, b);
+    d = __reduce_add_sync(fm, d);
+    if (lane == 0)
+    {
+      SumAcc* fa = acc + frame;
+      bool last = true;
+      if (slabs > 1)
+      {
+        atomicAdd(&fa->fails, a);
+        atomicAdd(&fa->sxFail, b);
+        atomicAdd(&fa->crossFail, d);
+        __threadfence();
+        last = (atomicAdd(&fa->done, 1u) == (uint32_t)slabs - 1u);
+        if (last)
+        {
+          __threadfence();
+          a = atomicExch(&fa->fails, 0u);
+          b = atomicExch(&fa->sxFail, 0u);
+          d = atomicExch(&fa->crossFail, 0u);
+          atomicExch(&fa->done, 0u);
+        }
+      }
+      if (last)
+        finalize_sum<KIND_OL>(g, p, a, b, 0u, d, out + frame, out);
+    }
+  }
+}
+
+static int sum_chunk_pixels(int kind) { return (kind == KIND_OL && (g_legacyLineKernel || g_widePlanarKernel)) ? 16 : 8; }
 
 int sum_sensor_block_threads(int kind, int width)
 {
@@ -705,7 +876,7 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
   if (grid > 0x7FFFFFFFLL)
     return cudaErrorInvalidValue;
   const int stages = g_sumStages;
-  const size_t ringBytes = (size_t)stages * threads * sizeof(uint4) * ((kind == KIND_OL && g_legacyLineKernel) ? 2 : 1);
+  const size_t ringBytes = (size_t)stages * threads * sizeof(uint4) * ((kind == KIND_OL && (g_legacyLineKernel || g_widePlanarKernel)) ? 2 : 1);
 #define TRIK_LAUNCH_SUM(K, ST)                                                                                   \
   do {                                                                                                           \
     if (ringBytes > 48 * 1024)                                                                                   \
@@ -753,7 +924,32 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
       if (g_legacyLineKernel) { TRIK_LAUNCH_SUM_KIND(KIND_WL); } else { TRIK_LAUNCH_V_KIND(false); }
       break;
     case KIND_OL:
-      if (g_legacyLineKernel) { TRIK_LAUNCH_SUM_KIND(KIND_OL); } else { TRIK_LAUNCH_V_KIND(true); }
+      if (g_widePlanarKernel)
+      {
+#define TRIK_LAUNCH_W(ST)                                                                                        \
+  do {                                                                                                           \
+    if (ringBytes > 48 * 1024)                                                                                   \
+      cudaFuncSetAttribute(vsum16_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);      \
+    cudaLaunchConfig_t cfg = {};                                                                                 \
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads);                                  \
+    cfg.dynamicSmemBytes = ringBytes; cfg.stream = stream;                                                       \
+    cudaLaunchAttribute attr[1];                                                                                 \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                             \
+    attr[0].val.programmaticStreamSerializationAllowed = 1;                                                      \
+    cfg.attrs = attr; cfg.numAttrs = g_overlapLaunch ? 1u : 0u;                                                  \
+    cudaLaunchKernelEx(&cfg, vsum16_kernel<ST>, g, frames, params, paramStride, acc, out, slabs, rowsPerSlab,    \
+                       cpr, rpi);                                                                                \
+  } while (0)
+        if (threads > 512) return cudaErrorInvalidValue;
+        switch (stages)
+        {
+          case 2: TRIK_LAUNCH_W(2); break;
+          case 4: TRIK_LAUNCH_W(4); break;
+          default: return cudaErrorInvalidValue;
+        }
+#undef TRIK_LAUNCH_W
+      }
+      else if (g_legacyLineKernel) { TRIK_LAUNCH_SUM_KIND(KIND_OL); } else { TRIK_LAUNCH_V_KIND(true); }
       break;
     case KIND_WO: TRIK_LAUNCH_SUM_KIND(KIND_WO); break;
     default:
