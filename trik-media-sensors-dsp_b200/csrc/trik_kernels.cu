@@ -16,6 +16,7 @@
 // independent, so shuffles + shared memory + one atomic per CTA per sum stay bit-exact.
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
+#include "trik_line.cuh"
 
 namespace trikb200 {
 
@@ -32,6 +33,7 @@ static int g_tuneStages = -1;
 static int g_tuneKernel = 0;
 static bool g_legacyLineKernel = false;      // resolved per launch
 static bool g_widePlanarKernel = false;      // resolved per launch: OL through vsum16_kernel
+static bool g_bulkLineKernel = false;        // resolved per launch: WL / OL through tsum_kernel (trik_kernels_line.cu)
 static int g_sumStages = 0;                  // resolved per launch
 void set_sum_stages(int v)
 {
@@ -39,20 +41,26 @@ void set_sum_stages(int v)
   g_tuneStages = v % 100;
   g_tuneKernel = v / 100;
 }
-static void resolve_tuning(int kind)
+static void resolve_tuning(int kind, int width)
 {
-  const bool tunedDefault = (kind == KIND_WL);
-  g_legacyLineKernel = g_tuneKernel == 1 ? true : (g_tuneKernel == 2 || g_tuneKernel == 3 ? false : !tunedDefault);
-  g_widePlanarKernel = kind == KIND_OL && g_tuneKernel == 3;
+  // measured defaults (profiles/): WL -> vsum_kernel, ring of 4; OL -> vsum16_kernel, ring of 4, from 320 columns
+  // up (narrower rows leave a thread too few iterations: first-version kernel, ring of 2); WO -> register prefetch
+  int kernel = g_tuneKernel;
+  if (kernel == 0)
+    kernel = kind == KIND_WL ? 2 : (kind == KIND_OL ? (width >= 320 ? 3 : 1) : 1);
+  g_legacyLineKernel = kernel == 1;
+  g_widePlanarKernel = kind == KIND_OL && kernel == 3;
+  g_bulkLineKernel = (kind == KIND_OL || kind == KIND_WL) && kernel == 4;
   if (g_tuneStages >= 0)
     g_sumStages = g_tuneStages;
   else
-    g_sumStages = kind == KIND_WL ? 4 : (kind == KIND_OL ? 2 : 0);
+    g_sumStages = kind == KIND_WL ? 4 : (kind == KIND_OL ? (g_widePlanarKernel ? 4 : 2) : 0);
 }
 extern long long g_launches_grid;
 extern long long g_launches_detect;
 extern long long g_launches_preview;
-long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview; }
+extern long long g_launches_line;
+long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line; }
 
 // ---------------------------------------------------------------------------------------------
 // per-pair work
@@ -77,68 +85,6 @@ __device__ __forceinline__ uint32_t hsvfail_pair(uint32_t yy, uint32_t cw, const
 {
   const uint32_t det = detect_pair_bits(yy, cw, coef, lutHue, lut255, bd, expected);
   return ((det & 1u) ^ 1u) | (((det >> 1) ^ 1u) << 16);
-}
-
-// ---------------------------------------------------------------------------------------------
-// finalisation: raw sums -> OutArgs, exactly the integer / float steps of the reference tails
-// ---------------------------------------------------------------------------------------------
-template <int KIND>
-__device__ void finalize_sum(const Geometry& g, const FrameParams& p, uint32_t fails, uint32_t sxFail,
-                             uint32_t syFail, uint32_t crossFail, TargetOut* o, const TargetOut* outBase)
-{
-  const uint32_t W = (uint32_t)g.width, H = (uint32_t)g.height;
-  TargetOut r;
-  DrawInfo di;
-  di.v[0] = 0; di.v[1] = 0; di.v[2] = 0; di.v[3] = 0;
-  r.targetX = 0; r.targetY = 0; r.targetSize = 0; r.pad = 0;
-  r.detectHue = r.detectHueTolerance = r.detectSat = r.detectSatTolerance = r.detectVal = r.detectValTolerance = 0;
-  if (KIND == KIND_WO)
-  {
-    const uint32_t points = W * H - fails;
-    const uint32_t sx = H * (W * (W - 1u) / 2u) - sxFail;
-    const uint32_t sy = W * (H * (H - 1u) / 2u) - syFail;
-    if (points > 0u)
-    {
-      const int32_t tx = (int32_t)(sx / points);
-      const int32_t ty = (int32_t)(sy / points);
-      const uint32_t radius = (uint32_t)ceilf(sqrtf((float)points / 3.1415927f));
-      r.targetX = (int8_t)(((tx - (int32_t)W / 2) * 100 * 2) / (int32_t)W);
-      r.targetY = (int8_t)(((ty - (int32_t)H / 2) * 100 * 2) / (int32_t)H);
-      r.targetSize = (uint8_t)((uint32_t)(radius * 100u * 4u) / (uint32_t)(W + H));
-      di.v[0] = 1; di.v[1] = tx; di.v[2] = ty; di.v[3] = (int32_t)radius;
-    }
-  }
-  else
-  {
-    const bool ol = (KIND == KIND_OL);
-    const uint32_t winW = ol ? (W - 9u) : W;                                   // OL counts columns 5..W-5 (:288)
-    const uint32_t colSum = ol ? ((W - 5u) * (W - 4u) / 2u - 10u) : (W * (W - 1u) / 2u);
-    const uint32_t points = winW * H - fails;
-    const uint32_t sx = H * colSum - sxFail;
-    uint32_t cross = 0;
-    if (ol)
-    {
-      uint32_t nrows = 0;
-      if (p.hStart <= p.hStop && p.hStart < H)
-        nrows = (p.hStop < H - 1u ? p.hStop : H - 1u) - p.hStart + 1u;
-      cross = winW * nrows - crossFail;
-    }
-    if (points > 10u)
-    {
-      const int32_t tx = (int32_t)(sx / points);
-      r.targetX = (int8_t)(((tx - (int32_t)W / 2) * 100 * 2) / (int32_t)W);
-      if (ol)
-        r.targetY = (int8_t)(int32_t)((uint32_t)(cross * 100u) / (uint32_t)(W * 2u * 40u));
-      r.targetSize = (uint8_t)((uint32_t)(points * 100u) / (uint32_t)(H * W));
-      di.v[0] = 1; di.v[1] = tx;
-    }
-  }
-  *o = r;
-  if (g.drawInfo)
-  {
-    int32_t* dv = static_cast<DrawInfo*>(g.drawInfo)[o - outBase].v;
-    dv[0] = di.v[0]; dv[1] = di.v[1]; dv[2] = di.v[2]; dv[3] = di.v[3];
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,57 +322,6 @@ sum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePara
 //     hStart..hStop, a contiguous run of a thread's iterations) is the difference of two snapshots
 //     of the accumulators -- nothing per pixel.
 // Per two pixels: 7 FMA-pipe + 6 ALU-pipe instructions in both layouts.
-// {N, N+1} lanes (pass, fail) of a pixel pair from its key lanes.
-// IMAD / IDP.4A issue on the FMA pipe and LOP3 / PRMT / VIADD / VIMNMX on the ALU pipe, both at one warp
-// instruction per two cycles per scheduler, so the pair is split 7 : 6 between them:
-//   FMA: 74*yy, three IDP.4A chroma terms, two replicate-and-add IMADs (red, green), one replicate IMAD (blue)
-//   ALU: luma extraction, VIADD.16x2 (blue, wraps like the reference's int16), VIMNMX3, VIADDMNMX, VIMNMX, VIADD.16x2 (count)
-__device__ __forceinline__ uint32_t vtest_lanes(uint32_t yy, uint32_t cw, const ChromaCoef cf,
-                                                uint32_t negKlo2, uint32_t n2, uint32_t cap2)
-{
-  const uint32_t y74 = yy * 74u;
-  const uint32_t cr = dp4a_uu(cw, cf.r, KEY_BIAS - 14248u);
-  const uint32_t cg = (uint32_t)dp4a_us(cw, cf.g, (int32_t)(KEY_BIAS + 8696u));
-  const uint32_t cb = dp4a_uu(cw, cf.b, KEY_BIAS - 17672u);
-  const uint32_t kr = cr * 0x10001u + y74;
-  const uint32_t kg = cg * 0x10001u + y74;
-  const uint32_t kb = __vadd2(cb * 0x10001u, y74);
-  const uint32_t km = __vimax3_u16x2(kr, kg, kb);
-  return __vminu2(__vmaxu2(__vadd2(km, negKlo2), n2), cap2);
-}
-
-// YUYV: measured slightly faster with the luma term folded into the dot product -- one IDP.4A per pixel
-// and channel yields the finished 32-bit key (74*Y + 102*V + c, ...), two keys are packed into lanes by
-// one IMAD (red, green: cannot overflow a lane) or one PRMT (blue: truncation to 16 bits IS the wrap).
-// 8 FMA-pipe + 5 ALU-pipe instructions per pair.
-__device__ __forceinline__ uint32_t vtest_yuyv(uint32_t w, uint32_t negKlo2, uint32_t n2, uint32_t cap2)
-{
-  const uint32_t r0 = dp4a_uu(w, 0x6600004Au, KEY_BIAS - 14248u);                       // 74*Y0 + 102*V + c
-  const uint32_t r1 = dp4a_uu(w, 0x664A0000u, KEY_BIAS - 14248u);                       // 74*Y1 + 102*V + c
-  const uint32_t g0 = (uint32_t)dp4a_us(w, 0xCC00E74Au, (int32_t)(KEY_BIAS + 8696u));   // 74*Y0 - 25*U - 52*V + c
-  const uint32_t g1 = (uint32_t)dp4a_us(w, 0xCC4AE700u, (int32_t)(KEY_BIAS + 8696u));
-  const uint32_t b0 = dp4a_uu(w, 0x0000814Au, KEY_BIAS - 17672u);                       // 74*Y0 + 129*U + c (may exceed 16 bits)
-  const uint32_t b1 = dp4a_uu(w, 0x004A8100u, KEY_BIAS - 17672u);
-  const uint32_t kr = r1 * 65536u + r0;
-  const uint32_t kg = g1 * 65536u + g0;
-  const uint32_t kb = __byte_perm(b0, b1, 0x5410);
-  const uint32_t km = __vimax3_u16x2(kr, kg, kb);
-  return __vminu2(__vmaxu2(__vadd2(km, negKlo2), n2), cap2);
-}
-
-// pair J (0/1) of a luma word L and the chroma word Cw under it
-template <int J>
-__device__ __forceinline__ uint32_t vtest_planar(uint32_t L, uint32_t Cw, uint32_t negKlo2, uint32_t n2, uint32_t cap2)
-{
-  return vtest_lanes(__byte_perm(L, 0u, J ? 0x4342 : 0x4140), Cw, J ? coef_planar1() : coef_planar0(), negKlo2, n2, cap2);
-}
-
-__device__ __forceinline__ uint32_t lanes_sub(uint32_t a, uint32_t b)      // lane-wise (a - b) mod 2^16
-{
-  return __vadd2(a, __vadd2(~b, 0x00010001u));
-}
-__device__ __forceinline__ uint32_t lanes_total(uint32_t a) { return (a & 0xFFFFu) + (a >> 16); }
-
 __device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc)
 {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
@@ -490,9 +385,11 @@ vsum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePar
   int itA = 0, itB = 0;
   if (PLANAR && p.hStart <= p.hStop)
   {
-    const long long a = (long long)p.hStart - firstRow, b = (long long)p.hStop + 1 - firstRow;
-    itA = a <= 0 ? 0 : (int)min((long long)iters, (a + rpi - 1) / rpi);
-    itB = b <= 0 ? 0 : (int)min((long long)iters, (b + rpi - 1) / rpi);
+    // rows past the image do not exist: clamp the band to it first, then 32-bit arithmetic is enough
+    const int a = (int)min(p.hStart, (uint32_t)g.height) - firstRow;
+    const int b = (int)min(p.hStop, (uint32_t)g.height - 1u) + 1 - firstRow;
+    itA = a <= 0 ? 0 : min(iters, (a + rpi - 1) / rpi);
+    itB = b <= 0 ? 0 : min(iters, (b + rpi - 1) / rpi);
   }
 
   uint32_t S0 = 0u, S1 = 0u, S2 = 0u, S3 = 0u;
@@ -659,8 +556,8 @@ vsum_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FramePar
 // per iteration.  Same bookkeeping as vsum_kernel (per-position {N, N+1} lanes, window folded into
 // the caps, cross band as a difference of snapshots).
 // ---------------------------------------------------------------------------------------------
-template <int STAGES>
-__global__ void __launch_bounds__(512, 2)
+template <int STAGES, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 vsum16_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
               const int paramStride, SumAcc* __restrict__ acc, TargetOut* __restrict__ out,
               const int slabs, const int rowsPerSlab, const int cpr, const int rpi)
@@ -698,67 +595,75 @@ vsum16_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   int itA = 0, itB = 0;
   if (p.hStart <= p.hStop)
   {
-    const long long a = (long long)p.hStart - firstRow, b = (long long)p.hStop + 1 - firstRow;
-    itA = a <= 0 ? 0 : (int)min((long long)iters, (a + rpi - 1) / rpi);
-    itB = b <= 0 ? 0 : (int)min((long long)iters, (b + rpi - 1) / rpi);
+    // rows past the image do not exist: clamp the band to it first, then 32-bit arithmetic is enough
+    const int a = (int)min(p.hStart, (uint32_t)g.height) - firstRow;
+    const int b = (int)min(p.hStop, (uint32_t)g.height - 1u) + 1 - firstRow;
+    itA = a <= 0 ? 0 : min(iters, (a + rpi - 1) / rpi);
+    itB = b <= 0 ? 0 : min(iters, (b + rpi - 1) / rpi);
   }
 
   uint32_t S0 = 0u, S1 = 0u, S2 = 0u, S3 = 0u, S4 = 0u, S5 = 0u, S6 = 0u, S7 = 0u;
   uint32_t snapA = 0u, snapB = 0u;
-  const int nthreads = (int)blockDim.x;
-  uint4* const mySlot = s_ring + t;
+  // explicit 32-bit shared addresses: slot s of this thread is slotBase + s * stageBytes (luma), + planeBytes (chroma)
+  const uint32_t planeBytes = blockDim.x * 16u, stageBytes = 2u * planeBytes;
+  const uint32_t slotBase = (uint32_t)__cvta_generic_to_shared(s_ring) + (uint32_t)t * 16u;
+  auto fill = [&](uint32_t slot)
+  {
+    const uint32_t dst = slotBase + slot * stageBytes;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(fillPtr) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + planeBytes), "l"(fillPtr + chromaOfs) : "memory");
+  };
 
   int fillIt = 0;
 #pragma unroll
   for (int sIdx = 0; sIdx < STAGES - 1; ++sIdx)
   {
     if (fillIt < iters)
-    {
-      cp_async16(mySlot + (sIdx * 2) * nthreads, fillPtr);
-      cp_async16(mySlot + (sIdx * 2 + 1) * nthreads, fillPtr + chromaOfs);
-    }
+      fill((uint32_t)sIdx);
     cp_async_commit();
     ++fillIt;
     fillPtr += rowStep;
   }
-  // three runs of iterations -- before, inside and after the cross band -- with a snapshot of the
-  // accumulators between them, so the band costs nothing per iteration
-  int it = 0;
-#pragma unroll 1
-  for (int seg = 0; seg < 3; ++seg)
+  // consume the chunk in ring slot `slot` (== iteration % STAGES) and request the one STAGES-1 iterations ahead
+  auto body = [&](const uint32_t slot)
   {
-    const int segEnd = seg == 0 ? itA : (seg == 1 ? itB : iters);
-#pragma unroll 1
-    for (; it < segEnd; ++it)
-    {
-      if (fillIt < iters)
-      {
-        const int fillSlot = (it + STAGES - 1) % STAGES;
-        cp_async16(mySlot + (fillSlot * 2) * nthreads, fillPtr);
-        cp_async16(mySlot + (fillSlot * 2 + 1) * nthreads, fillPtr + chromaOfs);
-      }
-      cp_async_commit();
-      ++fillIt;
-      fillPtr += rowStep;
-      cp_async_wait<STAGES - 1>();
-      const int slot = it % STAGES;
-      const uint4 L = mySlot[(slot * 2) * nthreads];
-      const uint4 Cw = mySlot[(slot * 2 + 1) * nthreads];
-      S0 = __vadd2(S0, vtest_planar<0>(L.x, Cw.x, negKlo2, n2, cap01));
-      S1 = __vadd2(S1, vtest_planar<1>(L.x, Cw.x, negKlo2, n2, cap01));
-      S2 = __vadd2(S2, vtest_planar<0>(L.y, Cw.y, negKlo2, n2, cap2));
-      S3 = __vadd2(S3, vtest_planar<1>(L.y, Cw.y, negKlo2, n2, np1));
-      S4 = __vadd2(S4, vtest_planar<0>(L.z, Cw.z, negKlo2, n2, np1));
-      S5 = __vadd2(S5, vtest_planar<1>(L.z, Cw.z, negKlo2, n2, np1));
-      S6 = __vadd2(S6, vtest_planar<0>(L.w, Cw.w, negKlo2, n2, cap67));
-      S7 = __vadd2(S7, vtest_planar<1>(L.w, Cw.w, negKlo2, n2, cap67));
-    }
-    if (seg < 2)
-    {
-      const uint32_t tot = __vadd2(__vadd2(__vadd2(S0, S1), __vadd2(S2, S3)), __vadd2(__vadd2(S4, S5), __vadd2(S6, S7)));
-      if (seg == 0) snapA = tot; else snapB = tot;
-    }
-  }
+    if (fillIt < iters)
+      fill((slot + STAGES - 1u) % STAGES);
+    cp_async_commit();
+    ++fillIt;
+    fillPtr += rowStep;
+    cp_async_wait<STAGES - 1>();
+    const uint32_t src = slotBase + slot * stageBytes;
+    uint4 L, Cw;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(L.x), "=r"(L.y), "=r"(L.z), "=r"(L.w) : "r"(src));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(Cw.x), "=r"(Cw.y), "=r"(Cw.z), "=r"(Cw.w) : "r"(src + planeBytes));
+    S0 = __vadd2(S0, vtest_planar<0>(L.x, Cw.x, negKlo2, n2, cap01));
+    S1 = __vadd2(S1, vtest_planar<1>(L.x, Cw.x, negKlo2, n2, cap01));
+    S2 = __vadd2(S2, vtest_planar<0>(L.y, Cw.y, negKlo2, n2, cap2));
+    S3 = __vadd2(S3, vtest_planar<1>(L.y, Cw.y, negKlo2, n2, np1));
+    S4 = __vadd2(S4, vtest_planar<0>(L.z, Cw.z, negKlo2, n2, np1));
+    S5 = __vadd2(S5, vtest_planar<1>(L.z, Cw.z, negKlo2, n2, np1));
+    S6 = __vadd2(S6, vtest_planar<0>(L.w, Cw.w, negKlo2, n2, cap67));
+    S7 = __vadd2(S7, vtest_planar<1>(L.w, Cw.w, negKlo2, n2, cap67));
+  };
+  auto lanes_sum = [&]() -> uint32_t
+  {
+    return __vadd2(__vadd2(__vadd2(S0, S1), __vadd2(S2, S3)), __vadd2(__vadd2(S4, S5), __vadd2(S6, S7)));
+  };
+  // three runs of iterations -- before, inside and after the cross band -- with a snapshot of the
+  // accumulators between them, so the band costs nothing per iteration (three copies of the loop measured
+  // faster than one copy driven by an outer loop, and than grouping iterations by ring depth)
+  auto run = [&](const int from, const int to)
+  {
+#pragma unroll 4
+    for (int it = from; it < to; ++it)
+      body((uint32_t)it % STAGES);
+  };
+  run(0, itA);
+  snapA = lanes_sum();
+  run(itA, itB);
+  snapB = lanes_sum();
+  run(itB, iters);
 
   const uint32_t total = __vadd2(__vadd2(__vadd2(S0, S1), __vadd2(S2, S3)), __vadd2(__vadd2(S4, S5), __vadd2(S6, S7)));
   (void)total;
@@ -822,7 +727,7 @@ vsum16_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   }
 }
 
-static int sum_chunk_pixels(int kind) { return (kind == KIND_OL && (g_legacyLineKernel || g_widePlanarKernel)) ? 16 : 8; }
+static int sum_chunk_pixels(int kind) { return (kind == KIND_OL && (g_legacyLineKernel || g_widePlanarKernel || g_bulkLineKernel)) ? 16 : 8; }
 
 int sum_sensor_block_threads(int kind, int width)
 {
@@ -849,7 +754,7 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
 {
   if (numFrames <= 0)
     return cudaSuccess;
-  resolve_tuning(kind);
+  resolve_tuning(kind, g.width);
   const int threads = sum_sensor_block_threads(kind, g.width);
   if (threads <= 0)
     return cudaErrorInvalidValue;
@@ -918,6 +823,14 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
     case 8: TRIK_LAUNCH_V(PL, 8); break;                        \
     default: return cudaErrorInvalidValue;                      \
   }
+  if (g_bulkLineKernel)
+  {
+    const cudaError_t e = launch_line_bulk(kind == KIND_OL, g, grid, threads, frames, params, paramStride, acc, out, slabs,
+                                           rowsPerSlab, cpr, rpi, stages, g_overlapLaunch != 0, stream);
+    if (e != cudaSuccess)
+      return e;
+    return cudaGetLastError();
+  }
   switch (kind)
   {
     case KIND_WL:
@@ -926,10 +839,10 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
     case KIND_OL:
       if (g_widePlanarKernel)
       {
-#define TRIK_LAUNCH_W(ST)                                                                                        \
+#define TRIK_LAUNCH_W2(ST, MT, MB)                                                                                       \
   do {                                                                                                           \
     if (ringBytes > 48 * 1024)                                                                                   \
-      cudaFuncSetAttribute(vsum16_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);      \
+      cudaFuncSetAttribute(vsum16_kernel<ST, MT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);  \
     cudaLaunchConfig_t cfg = {};                                                                                 \
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads);                                  \
     cfg.dynamicSmemBytes = ringBytes; cfg.stream = stream;                                                       \
@@ -937,17 +850,18 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                             \
     attr[0].val.programmaticStreamSerializationAllowed = 1;                                                      \
     cfg.attrs = attr; cfg.numAttrs = g_overlapLaunch ? 1u : 0u;                                                  \
-    cudaLaunchKernelEx(&cfg, vsum16_kernel<ST>, g, frames, params, paramStride, acc, out, slabs, rowsPerSlab,    \
+    cudaLaunchKernelEx(&cfg, vsum16_kernel<ST, MT, MB>, g, frames, params, paramStride, acc, out, slabs, rowsPerSlab,\
                        cpr, rpi);                                                                                \
   } while (0)
-        if (threads > 512) return cudaErrorInvalidValue;
+#define TRIK_LAUNCH_W(ST, MB) do { if (threads <= 256) TRIK_LAUNCH_W2(ST, 256, MB); else TRIK_LAUNCH_W2(ST, 1024, 1); } while (0)
         switch (stages)
         {
-          case 2: TRIK_LAUNCH_W(2); break;
-          case 4: TRIK_LAUNCH_W(4); break;
+          case 2: TRIK_LAUNCH_W(2, 4); break;
+          case 4: TRIK_LAUNCH_W(4, 4); break;
           default: return cudaErrorInvalidValue;
         }
 #undef TRIK_LAUNCH_W
+#undef TRIK_LAUNCH_W2
       }
       else if (g_legacyLineKernel) { TRIK_LAUNCH_SUM_KIND(KIND_OL); } else { TRIK_LAUNCH_V_KIND(true); }
       break;

@@ -101,6 +101,9 @@ int sum_sensor_block_threads(int kind, int width);
 void set_sum_stages(int stages);
 void set_target_threads(int threads);
 void set_overlap_launch(int on);
+cudaError_t launch_line_bulk(bool planar, const Geometry& g, long long grid, int threads, const uint8_t* frames,
+                             const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,
+                             int slabs, int rowsPerSlab, int cpr, int rpi, int stages, bool overlap, cudaStream_t stream);
 long long launch_count();
 
 } // namespace trikb200
