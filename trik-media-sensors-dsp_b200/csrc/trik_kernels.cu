@@ -765,9 +765,13 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
   int slabs = slabsPerFrame;
   if (slabs <= 0)
   {
-    const int wantCtas = 148 * 16;
+    // measured (profiles/r01k_tuning_slabs_small_batches.jsonl): one CTA per frame wins as soon as the frames
+    // alone fill the machine (~1480 resident CTAs); the wide YUV422P kernel has the costlier prologue and
+    // epilogue and wants >= 24 iterations per thread, the others >= 4
+    const int wantCtas = 148 * 12;
     slabs = (wantCtas + numFrames - 1) / numFrames;
-    const int maxSlabs = g.height / (rpi * 4) > 0 ? g.height / (rpi * 4) : 1;
+    const int minIters = g_widePlanarKernel ? 24 : 4;
+    const int maxSlabs = g.height / (rpi * minIters) > 0 ? g.height / (rpi * minIters) : 1;
     if (slabs > maxSlabs) slabs = maxSlabs;
     if (slabs < 1) slabs = 1;
   }
