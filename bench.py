@@ -240,6 +240,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # one process per GPU, bound to the GPU's NUMA node before any pinned buffer exists (e2e leg at N > 1)
+    from trik_media_sensors_dsp_b200 import sharding
+    bound = sharding.bind_to_gpu_numa(local_rank)
+
     n = args.batch
     fbytes = synth.frame_bytes(W, H, "yuyv")
     # this rank's shard of the stream: seeds rank*n .. rank*n + n - 1 (UNIQUE distinct frames, tiled)
@@ -374,7 +378,11 @@ def main():
             "repeat_ms_per_step": [r / args.steps for r in runs],
             "sustained": sustained,
         }
+        line["config"]["host_affinity"] = ("rank bound to its GPU's NUMA node: %d of %d CPUs" % (len(bound[1]), len(bound[0]))
+                                           if bound else "unbound (NVML affinity query unavailable)")
         if not args.no_cpu and world == 1:
+            if bound:
+                os.sched_setaffinity(0, bound[0])          # the CPU baseline uses every core of the box again
             cores = os.cpu_count() or 1
             fps1, n1, is_ref, _ = cpu_frames_per_sec(1, 128)
             fpsN, nN, _, _ = cpu_frames_per_sec(cores, 128)

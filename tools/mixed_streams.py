@@ -43,6 +43,8 @@ def main():
     from trik_media_sensors_dsp_b200 import open_sensor, process_mixed, sensors, sharding, synth, xdm, launch_count
 
     torch.cuda.set_device(local_rank)
+    from trik_media_sensors_dsp_b200 import sharding as _sh
+    _sh.bind_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sensors.lib().trikb200_setDevice(local_rank)
