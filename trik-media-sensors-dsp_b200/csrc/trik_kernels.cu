@@ -14,13 +14,14 @@
 // sums collapse to (fail count) * column + (tiny packed in-chunk sums) at the very end, and a
 // warp's 32 loads are one contiguous 512-byte run of a row.  All sums are integer and order
 // independent, so shuffles + shared memory + one atomic per CTA per sum stay bit-exact.
+#include <atomic>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 #include "trik_line.cuh"
 
 namespace trikb200 {
 
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
 // Tuning state.  Default (-1): the measured best per sensor on B200 --
 //   WL: tuned line kernel, cp.async ring of 4;  OL: first-version kernel, ring of 2;  WO: register prefetch.
 // trikb200_setLoadStages(v): v % 100 = load path (0 register prefetch, 2 / 4 ring depth),
@@ -31,10 +32,11 @@ static int g_overlapLaunch = 1;              // programmatic dependent launch of
 void set_overlap_launch(int on) { g_overlapLaunch = on ? 1 : 0; }
 static int g_tuneStages = -1;
 static int g_tuneKernel = 0;
-static bool g_legacyLineKernel = false;      // resolved per launch
-static bool g_widePlanarKernel = false;      // resolved per launch: OL through vsum16_kernel
-static bool g_bulkLineKernel = false;        // resolved per launch: WL / OL through tsum_kernel (trik_kernels_line.cu)
-static int g_sumStages = 0;                  // resolved per launch
+// resolved per launch from the knobs above; thread_local so that host threads driving different handles do not race
+static thread_local bool g_legacyLineKernel = false;
+static thread_local bool g_widePlanarKernel = false;      // resolved per launch: OL through vsum16_kernel
+static thread_local bool g_bulkLineKernel = false;        // resolved per launch: WL / OL through tsum_kernel (trik_kernels_line.cu)
+static thread_local int g_sumStages = 0;
 void set_sum_stages(int v)
 {
   if (v < 0) { g_tuneStages = -1; g_tuneKernel = 0; return; }
@@ -56,10 +58,10 @@ static void resolve_tuning(int kind, int width)
   else
     g_sumStages = kind == KIND_WL ? 4 : (kind == KIND_OL ? (g_widePlanarKernel ? 4 : 2) : 0);
 }
-extern long long g_launches_grid;
-extern long long g_launches_detect;
-extern long long g_launches_preview;
-extern long long g_launches_line;
+extern std::atomic<long long> g_launches_grid;
+extern std::atomic<long long> g_launches_detect;
+extern std::atomic<long long> g_launches_preview;
+extern std::atomic<long long> g_launches_line;
 long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line; }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,13 +18,14 @@
 // Rows are replayed in order by one CTA per frame; everything inside a row is parallel.
 //
 // The annealing that follows (9200 moves driven by rand()/pow()) runs on the host: see trik_host.cpp.
+#include <atomic>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 
 namespace trikb200 {
 
-extern long long g_launches_detect;
-long long g_launches_detect = 0;
+extern std::atomic<long long> g_launches_detect;
+std::atomic<long long> g_launches_detect{0};
 
 // ---------------------------------------------------------------------------------------------
 // WO

@@ -15,13 +15,14 @@
 //     The labelling is order dependent by construction (non-transitive equivalences, the first
 //     pixel of a label is not counted, merge in label order, std::sort tie order), so it is
 //     replayed step for step by one lane per frame; frames run in parallel.
+#include <atomic>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 
 namespace trikb200 {
 
-extern long long g_launches_grid;
-long long g_launches_grid = 0;
+extern std::atomic<long long> g_launches_grid;
+std::atomic<long long> g_launches_grid{0};
 
 // threads per CTA = chunksPerRow * rowsPerIteration, about `target` threads, a multiple of 32 when possible
 static int rows_per_iteration(int cpr, int target)

@@ -12,13 +12,14 @@
 //
 //   WL  webcam/line_sensor/include/internal/cv_line_detector_seqpass.hpp:197-269, tail :401-417
 //   OL  ov7670/line_sensor/include/internal/cv_line_detector_seqpass.hpp:210-301, tail :449-473
+#include <atomic>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 #include "trik_line.cuh"
 
 namespace trikb200 {
 
-long long g_launches_line = 0;
+std::atomic<long long> g_launches_line{0};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

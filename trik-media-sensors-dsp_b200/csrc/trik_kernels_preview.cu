@@ -15,13 +15,14 @@
 // inverse maps with the reference's own double arithmetic and every destination pixel is produced exactly
 // once, coalesced.  Overlays are replayed per frame by one warp: primitives in reference order, the pixels
 // of one primitive (one colour) spread over the lanes.
+#include <atomic>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 
 namespace trikb200 {
 
-extern long long g_launches_preview;
-long long g_launches_preview = 0;
+extern std::atomic<long long> g_launches_preview;
+std::atomic<long long> g_launches_preview{0};
 
 __device__ __forceinline__ uint16_t rgb565x(uint32_t rgb888)           // writeOutputPixel (:66-70)
 {
