@@ -259,6 +259,9 @@ void trikb200_setBlockThreads(XDAS_Int32 threads);
  * CTAs are placed while the previous batch drains (each kernel still waits for all earlier work of the stream
  * before its first memory access); 0 = plain launches */
 void trikb200_setOverlapLaunch(XDAS_Int32 on);
+/* tuning knob: webcam object sensor batches whose frames share one threshold set can run through a chroma-indexed
+ * detection table (results identical): 0 = automatic (default), 1 = whenever possible, -1 = never */
+void trikb200_setLutMode(XDAS_Int32 mode);
 /* last CUDA / argument error message of this thread ("" if none) */
 const char* trikb200_lastError(void);
 
@@ -268,6 +271,10 @@ const char* trikb200_lastError(void);
  * -> 0x00VVSSHH through the packed two-pixel path the sensors use (bit 31: lane paths disagree).
  * hostOut holds count words. */
 XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count, uint32_t* hostOut);
+/* diagnostics for the parity tests: build the chroma-indexed detection table of a webcam object sensor threshold
+ * set and compare it with the arithmetic on all 2^24 (Y,U,V).  stats[0] = mismatching pixels (must be 0),
+ * [1] / [2] / [3] = chroma entries that never pass / pass on one luma interval / need the mask, [4] = passing pixels. */
+XDAS_Int32 trikb200_probeLut(const TRIKB200_RangeInArgsAlg* inArgsAlg, uint64_t stats[5]);
 
 #ifdef __cplusplus
 }

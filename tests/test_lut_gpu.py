@@ -1,0 +1,80 @@
+"""The chroma-indexed detection table of the webcam object sensor (csrc/trik_kernels_lut.cu): the table must
+reproduce the arithmetic threshold on ALL 2^24 (Y,U,V) inputs for every threshold set tried, and the sensor
+run through it must give the oracle's bytes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import ref as oracle
+from trik_media_sensors_dsp_b200 import lib, open_sensor, synth, xdm
+
+pytestmark = pytest.mark.gpu
+
+THRESHOLDS = [
+    (300, 40, 20, 100, 30, 100, 0),    # hue wraps through 0
+    (90, 150, 35, 100, 35, 100, 0),    # green-ish
+    (0, 359, 0, 100, 0, 100, 0),       # everything
+    (0, 359, 0, 100, 0, 40, 0),        # dark
+    (200, 260, 40, 100, 20, 90, 0),
+    (10, 20, 50, 60, 50, 60, 0),       # narrow in all three
+    (0, 0, 0, 0, 60, 30, 0),           # empty value range
+    (350, 10, 0, 10, 90, 100, 0),      # near-white reds
+    (120, 120, 50, 50, 50, 50, 0),     # single values
+]
+
+
+@pytest.fixture(autouse=True)
+def _defaults_after():
+    yield
+    lib().trikb200_setLutMode(0)
+
+
+@pytest.mark.parametrize("args", THRESHOLDS)
+def test_table_equals_arithmetic_on_all_inputs(args):
+    ia = xdm.RangeInArgsAlg(*args)
+    stats = (C.c_uint64 * 5)()
+    assert lib().trikb200_probeLut(C.addressof(ia), C.addressof(stats)) == 0, lib().trikb200_lastError()
+    mismatches, never, interval, ragged, passing = [int(v) for v in stats]
+    assert never + interval + ragged == 65536
+    assert mismatches == 0, (args, mismatches, never, interval, ragged, passing)
+
+
+@pytest.mark.parametrize("size", [(320, 240), (640, 480), (160, 120), (32, 4), (96, 8), (1280, 720), (640, 44)])
+def test_wo_through_table_matches_oracle(size):
+    w, h = size
+    fams = [("noise", s) for s in range(3)] + [("scene", s) for s in range(4)] + [(e, 0) for e in synth.EDGE_CASES]
+    if w < 64 or h < 16:
+        fams = [("noise", s) for s in range(4)] + [("zero", 0), ("full", 0), ("bluewrap", 0), ("greyramp", 0)]
+    frames = np.stack([synth.make_frame(f, s, w, h, "yuyv") for f, s in fams])
+    frames = np.concatenate([frames] * 3)                       # more frames than one CTA's groups
+    codec = open_sensor("wo", w, h)
+    for args in THRESHOLDS:
+        orc = oracle.OracleSensor("wo", w, h)
+        want = [bytes(memoryview(orc.process(frames[i], oracle.RangeInArgs(*args))[1]))[:3] for i in range(len(fams))] * 3
+        for mode in (1, -1):
+            lib().trikb200_setLutMode(mode)
+            before = lib().trikb200_launchCount()
+            ret, outs = codec.process_batch(frames, xdm.RangeInArgsAlg(*args))
+            assert ret == 0, lib().trikb200_lastError()
+            got = [bytes(memoryview(o))[:3] for o in outs]
+            assert got == want, (size, args, mode, [i for i in range(len(got)) if got[i] != want[i]][:8])
+    codec.close()
+
+
+def test_table_is_reused_and_rebuilt():
+    """Same thresholds -> one table build; new thresholds -> a new build; large batches pick the table on their own."""
+    w, h = 320, 240
+    frames = np.stack([synth.make_frame("scene", s % 7, w, h, "yuyv") for s in range(256)])
+    codec = open_sensor("wo", w, h)
+    a1, a2 = xdm.RangeInArgsAlg(300, 40, 20, 100, 30, 100, 0), xdm.RangeInArgsAlg(90, 150, 35, 100, 35, 100, 0)
+    lib().trikb200_setLutMode(0)
+    n0 = lib().trikb200_launchCount()
+    assert codec.process_batch(frames, a1)[0] == 0
+    n1 = lib().trikb200_launchCount()
+    assert codec.process_batch(frames, a1)[0] == 0
+    n2 = lib().trikb200_launchCount()
+    assert codec.process_batch(frames, a2)[0] == 0
+    n3 = lib().trikb200_launchCount()
+    assert (n1 - n0, n2 - n1, n3 - n2) == (2, 1, 2)            # build + pass, pass, build + pass
+    codec.close()

@@ -26,6 +26,7 @@ namespace {
 thread_local std::string t_lastError;
 thread_local int t_device = -1;
 int g_slabsPerFrame = 0;
+int g_lutMode = 0;                 // 0 auto, 1 whenever the arguments are shared by the batch, -1 never
 
 void set_error(const char* what, cudaError_t e = cudaSuccess)
 {
@@ -124,6 +125,10 @@ struct Instance {
   uint16_t*    dEqual = nullptr;    size_t dEqualCap = 0;      // OO label equivalences
   int*         dFlagged = nullptr;  size_t dFlaggedCap = 0;    // indices of frames that auto-calibrate
   int32_t*     dHist = nullptr;     size_t dHistCap = 0;       // ordered +1/-2 histograms (int32 entries)
+  // chroma-indexed detection table of the last threshold set (WO batches, trik_kernels_lut.cu)
+  uint16_t*    dLutTable = nullptr; uint32_t* dLutMasks = nullptr;
+  uint32_t     lutFrom = 0, lutTo = 0, lutExpected = 0; bool lutValid = false; cudaStream_t lutStream = nullptr;
+  int          smCount = 0;
   // preview (RGB565X) support: index maps of this geometry, overlay inputs, staging image
   int32_t*     dHi2ho = nullptr;  int32_t* dWi2wo = nullptr;   // source row/col -> preview row/col
   int32_t*     dLastRow = nullptr; int32_t* dLastCol = nullptr; // preview row/col -> last source row/col (-1: none)
@@ -148,6 +153,7 @@ struct Instance {
     if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); stream = nullptr; }
     cudaFree(dFrames); dFrames = nullptr; dFramesCap = 0;
     cudaFree(dParams); dParams = nullptr; dParamsCap = 0;
+    cudaFree(dLutTable); dLutTable = nullptr; cudaFree(dLutMasks); dLutMasks = nullptr; lutValid = false;
     cudaFree(dAcc);    dAcc = nullptr;    dAccCap = 0;
     cudaFree(dOut);    dOut = nullptr;    dOutCap = 0;
     cudaFree(dMxnTable); dMxnTable = nullptr;
@@ -534,10 +540,40 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
   switch (kind)
   {
     case KIND_WO: case KIND_WL: case KIND_OL:
-      if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
-      CUDA_TRY(launch_sum_sensor(kind, g, b.n, dFrames, in->dParams, pstride, in->dAcc,
-                                 reinterpret_cast<TargetOut*>(dOut), g_slabsPerFrame, s));
+    {
+      // WO batches that share one threshold set go through the chroma table (built once per set, kept with the
+      // handle); below ~256 frames building it costs more than it saves unless it is already there
+      bool useLut = false;
+      if (kind == KIND_WO && broadcast && g_lutMode >= 0 && g.width % 8 == 0)
+      {
+        const FrameParams& fp = in->paramsScratch[0];
+        const bool have = in->lutValid && in->lutStream == s && in->lutFrom == fp.from && in->lutTo == fp.to
+                          && in->lutExpected == fp.expected;
+        useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32);
+        if (useLut && !have)
+        {
+          if (!in->dLutTable)
+          {
+            CUDA_TRY(cudaMalloc(&in->dLutTable, LUT_TABLE_BYTES));
+            CUDA_TRY(cudaMalloc(&in->dLutMasks, LUT_MASK_BYTES));
+            CUDA_TRY(cudaDeviceGetAttribute(&in->smCount, cudaDevAttrMultiProcessorCount, in->device));
+          }
+          CUDA_TRY(launch_chroma_table(fp.from, fp.to, fp.expected, in->dLutTable, in->dLutMasks, s));
+          in->lutFrom = fp.from; in->lutTo = fp.to; in->lutExpected = fp.expected;
+          in->lutValid = true; in->lutStream = s;
+        }
+      }
+      if (useLut)
+        CUDA_TRY(launch_wo_lut(g, b.n, dFrames, in->dParams, in->dLutTable, in->dLutMasks,
+                               reinterpret_cast<TargetOut*>(dOut), in->smCount, s));
+      else
+      {
+        if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
+        CUDA_TRY(launch_sum_sensor(kind, g, b.n, dFrames, in->dParams, pstride, in->dAcc,
+                                   reinterpret_cast<TargetOut*>(dOut), g_slabsPerFrame, s));
+      }
       break;
+    }
     case KIND_OM:
       if (b.outOnDevice)
         CUDA_TRY(cudaMemsetAsync(dOut, 0, recBytes * b.n, s));
@@ -1305,6 +1341,7 @@ void trikb200_setSlabsPerFrame(XDAS_Int32 slabs) { g_slabsPerFrame = slabs; }
 void trikb200_setLoadStages(XDAS_Int32 stages) { set_sum_stages(stages); }
 void trikb200_setBlockThreads(XDAS_Int32 threads) { set_target_threads(threads); }
 void trikb200_setOverlapLaunch(XDAS_Int32 on) { set_overlap_launch(on); }
+void trikb200_setLutMode(XDAS_Int32 mode) { g_lutMode = mode; }
 const char* trikb200_lastError(void) { return t_lastError.c_str(); }
 
 /* test probes: exhaustive pixel functions straight from the device code (tests/test_pixel_gpu.py) */
@@ -1321,6 +1358,29 @@ XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count
   if (e != cudaSuccess)
   {
     set_error("probe", e);
+    return IVIDTRANSCODE_EFAIL;
+  }
+  return IVIDTRANSCODE_EOK;
+}
+
+XDAS_Int32 trikb200_probeLut(const TRIKB200_RangeInArgsAlg* inArgsAlg, uint64_t stats[5])
+{
+  Geometry g{};
+  CarriedState st{};
+  FrameParams fp;
+  prepare_frame_params(KIND_WO, g, inArgsAlg, st, fp);
+  uint16_t* table = nullptr; uint32_t* masks = nullptr; unsigned long long* dStats = nullptr;
+  cudaError_t e = cudaMalloc(&table, LUT_TABLE_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc(&masks, LUT_MASK_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc(&dStats, 5 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(dStats, 0, 5 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = launch_chroma_table(fp.from, fp.to, fp.expected, table, masks, 0);
+  if (e == cudaSuccess) e = launch_lut_check(fp.from, fp.to, fp.expected, table, masks, dStats, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(stats, dStats, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(table); cudaFree(masks); cudaFree(dStats);
+  if (e != cudaSuccess)
+  {
+    set_error("probeLut", e);
     return IVIDTRANSCODE_EFAIL;
   }
   return IVIDTRANSCODE_EOK;
