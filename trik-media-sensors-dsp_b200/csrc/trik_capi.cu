@@ -126,7 +126,7 @@ struct Instance {
   int*         dFlagged = nullptr;  size_t dFlaggedCap = 0;    // indices of frames that auto-calibrate
   int32_t*     dHist = nullptr;     size_t dHistCap = 0;       // ordered +1/-2 histograms (int32 entries)
   // chroma-indexed detection table of the last threshold set (WO batches, trik_kernels_lut.cu)
-  uint16_t*    dLutTable = nullptr; uint32_t* dLutMasks = nullptr;
+  uint8_t*     dLutTable = nullptr; uint32_t* dLutMasks = nullptr;
   uint32_t     lutFrom = 0, lutTo = 0, lutExpected = 0; bool lutValid = false; cudaStream_t lutStream = nullptr;
   int          smCount = 0;
   // preview (RGB565X) support: index maps of this geometry, overlay inputs, staging image
@@ -1369,7 +1369,7 @@ XDAS_Int32 trikb200_probeLut(const TRIKB200_RangeInArgsAlg* inArgsAlg, uint64_t 
   CarriedState st{};
   FrameParams fp;
   prepare_frame_params(KIND_WO, g, inArgsAlg, st, fp);
-  uint16_t* table = nullptr; uint32_t* masks = nullptr; unsigned long long* dStats = nullptr;
+  uint8_t* table = nullptr; uint32_t* masks = nullptr; unsigned long long* dStats = nullptr;
   cudaError_t e = cudaMalloc(&table, LUT_TABLE_BYTES);
   if (e == cudaSuccess) e = cudaMalloc(&masks, LUT_MASK_BYTES);
   if (e == cudaSuccess) e = cudaMalloc(&dStats, 5 * sizeof(unsigned long long));

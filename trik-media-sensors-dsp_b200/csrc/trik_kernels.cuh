@@ -101,15 +101,15 @@ int sum_sensor_block_threads(int kind, int width);
 void set_sum_stages(int stages);
 void set_target_threads(int threads);
 void set_overlap_launch(int on);
-// chroma-indexed detection table (trik_kernels_lut.cu): 65 536 x uint16 + 65 536 x 8 x uint32
-constexpr size_t LUT_TABLE_BYTES = 65536 * sizeof(uint16_t);
+// chroma-indexed detection table (trik_kernels_lut.cu): 2 x 65 536 bytes + 65 536 x 8 x uint32
+constexpr size_t LUT_TABLE_BYTES = 2 * 65536;
 constexpr size_t LUT_MASK_BYTES  = (size_t)65536 * 8 * sizeof(uint32_t);
-cudaError_t launch_chroma_table(uint32_t from, uint32_t to, uint32_t expected, uint16_t* table, uint32_t* masks,
+cudaError_t launch_chroma_table(uint32_t from, uint32_t to, uint32_t expected, uint8_t* table, uint32_t* masks,
                                 cudaStream_t stream);
-cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, const uint16_t* table, const uint32_t* masks,
+cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, const uint8_t* table, const uint32_t* masks,
                              unsigned long long* stats, cudaStream_t stream);
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
-                          const uint16_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream);
+                          const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream);
 cudaError_t launch_line_bulk(bool planar, const Geometry& g, long long grid, int threads, const uint8_t* frames,
                              const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,
                              int slabs, int rowsPerSlab, int cpr, int rpi, int stages, bool overlap, cudaStream_t stream);

@@ -9,15 +9,16 @@
 //   chroma_table_kernel   evaluates the exact arithmetic (detect_pair_bits, the same code the direct kernels
 //                         run) on all 2^24 (Y,U,V) once per threshold set: 65 536 warps, one per chroma pair,
 //                         each producing the 256-bit pass mask over Y.  It writes
-//                           table[U | V<<8] = lo | hi<<8   when the mask is exactly the interval lo..hi,
-//                                             NEVER        when no luma passes,
-//                                             RAGGED       otherwise (rounding jitter near a hue / saturation
-//                                                          bound: 1..10 % of the entries),
+//                           lo[U | V<<8], nhi[U | V<<8] = lo, 255 - hi   when the mask is exactly the interval lo..hi,
+//                                                         NEVER          when no luma passes,
+//                                                         RAGGED         otherwise (rounding jitter near a hue /
+//                                                                        saturation bound: 1..10 % of the entries),
 //                         and the 256-bit masks themselves (2 MB, L2 resident) for the RAGGED entries.
-//   wo_lut_kernel         the WO pass with the 128 KB table in shared memory: per pixel pair one 16-bit LDS and
-//                         two packed compares instead of the HSV arithmetic; a warp that meets a RAGGED entry
-//                         fetches the mask word of those pixels from L2.  ~17 instructions per pair, the same
-//                         budget as the line kernels.  The CTA is persistent (one per SM, the table is loaded
+//   wo_lut_kernel         the WO pass with the two 64 KB byte tables in shared memory: per pixel pair two byte LDS
+//                         and two packed compares instead of the HSV arithmetic; a warp that meets a RAGGED entry
+//                         fetches the mask word of those pixels from L2.  The work is split between the ALU pipe
+//                         (byte extraction, guard lanes, final AND) and the FMA pipe (the compares and all
+//                         accumulation are IMAD / IMAD.HI), ~17 instructions per pair like the line kernels.  The CTA is persistent (one per SM, the table is loaded
 //                         once) and is split into independent groups of threads, one frame per group at a
 //                         time, synchronised by named barriers.
 //
@@ -32,15 +33,17 @@ namespace trikb200 {
 
 std::atomic<long long> g_launches_lut{0};
 
-constexpr uint32_t LUT_NEVER  = 0x00FFu;      // lo = 255, hi = 0: no luma can satisfy lo <= Y <= hi
-constexpr uint32_t LUT_RAGGED = 0x01FFu;      // lo = 255, hi = 1: fails the interval test too, marks "consult the mask"
+// (lo, nhi = 255 - hi) codes with lo > hi: no luma satisfies lo <= Y <= hi, so the interval test fails by itself
+constexpr uint32_t LUT_NEVER_LO = 255u, LUT_NEVER_NHI = 255u;        // hi = 0
+constexpr uint32_t LUT_RAGGED_LO = 255u, LUT_RAGGED_NHI = 254u;      // hi = 1: marks "consult the mask"
+constexpr uint32_t LUT_RAGGED_CODE = LUT_RAGGED_LO * 256u + LUT_RAGGED_NHI;     // lo * 256 + nhi
 
 // ---------------------------------------------------------------------------------------------
 // table construction: one warp per chroma pair
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 chroma_table_kernel(const uint32_t from, const uint32_t to, const uint32_t expected,
-                    uint16_t* __restrict__ table, uint32_t* __restrict__ masks)
+                    uint8_t* __restrict__ table, uint32_t* __restrict__ masks)
 {
   __shared__ HueLutEntry s_lutHue[256];
   __shared__ uint16_t s_lut43[256];
@@ -79,7 +82,10 @@ chroma_table_kernel(const uint32_t from, const uint32_t to, const uint32_t expec
     }
   }
   if (lane == 0u)
-    table[idx] = (uint16_t)(count == 0u ? LUT_NEVER : (rises == 1u ? (lo | (hi << 8)) : LUT_RAGGED));
+  {
+    table[idx]          = (uint8_t)(count == 0u ? LUT_NEVER_LO : (rises == 1u ? lo : LUT_RAGGED_LO));
+    table[65536u + idx] = (uint8_t)(count == 0u ? LUT_NEVER_NHI : (rises == 1u ? 255u - hi : LUT_RAGGED_NHI));
+  }
   if (lane < 8u)
   {
     uint32_t mine = w[0];
@@ -90,7 +96,7 @@ chroma_table_kernel(const uint32_t from, const uint32_t to, const uint32_t expec
   }
 }
 
-cudaError_t launch_chroma_table(uint32_t from, uint32_t to, uint32_t expected, uint16_t* table, uint32_t* masks,
+cudaError_t launch_chroma_table(uint32_t from, uint32_t to, uint32_t expected, uint8_t* table, uint32_t* masks,
                                 cudaStream_t stream)
 {
   chroma_table_kernel<<<65536 / 8, 256, 0, stream>>>(from, to, expected, table, masks);
@@ -106,17 +112,26 @@ __device__ __forceinline__ void group_barrier(int id, int count)
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
 }
 
-// fail lanes {0,1} of a YUYV pixel pair from its table entry: pass <=> lo <= Y <= hi.
-// Guard bit 15 in every lane keeps the two 16-bit subtractions of one 32-bit SUB apart (no borrow can leave a
-// lane: 0x8000 + Y - lo >= 0x7F01) and doubles as the result: bit 15 stays set <=> the difference is >= 0.
-__device__ __forceinline__ uint32_t lut_fail_pair(uint32_t word, uint32_t entry)
+// Pass bits of a YUYV pixel pair (bit 15: pixel 0, bit 31: pixel 1) from its table entry: pass <=> lo <= Y <= hi.
+// Guard bit 15 in every 16-bit lane keeps the two subtractions of one 32-bit operation apart (0x8000 + a - b with
+// bytes a, b never borrows) and doubles as the result: it stays set <=> a >= b.  Y <= hi is tested as
+// 255 - Y >= 255 - hi, so that both compares are one IMAD each (lane replication by 0x10001 included).
+__device__ __forceinline__ uint32_t lut_pass_pair(uint32_t word, uint32_t lo, uint32_t nhi)
 {
-  const uint32_t yyG = (word & 0x00FF00FFu) | 0x80008000u;
-  const uint32_t lo2 = __byte_perm(entry, 0u, 0x4040);                 // lo in both lanes
-  const uint32_t hiG = __byte_perm(entry, 0x00000080u, 0x4141);        // 0x8000 + hi in both lanes
-  const uint32_t geLo = yyG - lo2;                                     // bit 15 of a lane <=> Y >= lo
-  const uint32_t leHi = hiG - (word & 0x00FF00FFu);                    // bit 15 of a lane <=> Y <= hi
-  return (~(geLo & leHi) & 0x80008000u) >> 15;
+  const uint32_t yG  = (word & 0x00FF00FFu) | 0x80008000u;             // 0x8000 + Y per lane
+  const uint32_t nyG = (~word & 0x00FF00FFu) | 0x80008000u;            // 0x8000 + 255 - Y per lane
+  const uint32_t geLo = yG - lo * 0x00010001u;
+  const uint32_t leHi = nyG - nhi * 0x00010001u;
+  return geLo & leHi & 0x80008000u;
+}
+
+// pass bits of a pair whose entry is RAGGED: the luma masks decide
+__device__ __forceinline__ uint32_t lut_pass_pair_masks(uint32_t word, uint32_t ci, const uint32_t* __restrict__ masks)
+{
+  const uint32_t y0 = word & 0xFFu, y1 = (word >> 16) & 0xFFu;
+  const uint32_t m0 = __ldg(masks + (size_t)ci * 8u + (y0 >> 5));
+  const uint32_t m1 = __ldg(masks + (size_t)ci * 8u + (y1 >> 5));
+  return (((m0 >> (y0 & 31u)) & 1u) << 15) | (((m1 >> (y1 & 31u)) & 1u) << 31);
 }
 
 // Persistent CTA: `groups` independent groups of `gthreads` threads, one frame per group at a time.
@@ -124,11 +139,11 @@ __device__ __forceinline__ uint32_t lut_fail_pair(uint32_t word, uint32_t entry)
 template <int STAGES>
 __global__ void __launch_bounds__(1024, 1)
 wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
-              const uint16_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
+              const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
               const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi)
 {
   extern __shared__ __align__(16) uint8_t s_raw[];
-  uint16_t* const s_table = reinterpret_cast<uint16_t*>(s_raw);                       // 65 536 entries
+  uint8_t* const s_table = s_raw;                                                      // lo[65536], nhi[65536]
   uint4* const s_ring = reinterpret_cast<uint4*>(s_raw + 131072);                     // [STAGES][groups * gthreads]
   uint32_t* const s_red = reinterpret_cast<uint32_t*>(s_raw + 131072 + (size_t)STAGES * groups * gthreads * 16);   // [groups][32][4]
 
@@ -151,86 +166,101 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   const int warpInGroup = tg >> 5, lane = tg & 31, gwarps = gthreads >> 5;
   const int itersAll = rr < g.height ? (g.height - rr + rpi - 1) / rpi : 0;
   const size_t rowStep = (size_t)rpi * g.lineLength;
-  const int ringThreads = groups * gthreads;
-  uint4* const mySlot = s_ring + t;
+  const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(s_table);
+  const uint32_t stageBytes = (uint32_t)(groups * gthreads) * 16u;
+  const uint32_t slotBase = (uint32_t)__cvta_generic_to_shared(s_ring) + (uint32_t)t * 16u;
   uint32_t* const myRed = s_red + group * 128;
   const FrameParams p = params[0];
+  const uint32_t W = (uint32_t)g.width, H = (uint32_t)g.height;
 
   for (int frame = blockIdx.x * groups + group; frame < numFrames; frame += gridDim.x * groups)
   {
     const uint8_t* fillPtr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)rr * g.lineLength;
-    uint32_t fails = 0u, inIdx = 0u, syFail = 0u;        // 32-bit totals of this thread
+    uint32_t passes = 0u, inIdx = 0u, syPass = 0u;       // 32-bit totals of this thread
     int fillIt = 0;
 #pragma unroll
     for (int sIdx = 0; sIdx < STAGES - 1; ++sIdx)
     {
       if (fillIt < itersAll)
-        cp_async16(mySlot + sIdx * ringThreads, fillPtr);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(slotBase + (uint32_t)sIdx * stageBytes), "l"(fillPtr) : "memory");
       cp_async_commit();
       ++fillIt;
       fillPtr += rowStep;
     }
-    // packed 16-bit lane sums are flushed every 128 iterations (SI <= 8 * 128 * 127 / 2 < 2^16)
-    for (int seg0 = 0; seg0 < itersAll; seg0 += 128)
+    uint32_t S = 0u, A = 0u, SI = 0u;                    // packed 16-bit lane sums of the current segment
+    // one row chunk: ring slot `slot` holds it, `j` is its iteration number inside the segment
+    auto body = [&](const uint32_t slot, const uint32_t j)
     {
-      const int segN = min(128, itersAll - seg0);
-      uint32_t S = 0u, A = 0u, SI = 0u;
-      for (int j = 0; j < segN; ++j)
+      if (fillIt < itersAll)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(slotBase + ((slot + STAGES - 1u) % STAGES) * stageBytes), "l"(fillPtr) : "memory");
+      cp_async_commit();
+      ++fillIt;
+      fillPtr += rowStep;
+      cp_async_wait<STAGES - 1>();
+      uint32_t wd[4];
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wd[0]), "=r"(wd[1]), "=r"(wd[2]), "=r"(wd[3]) : "r"(slotBase + slot * stageBytes));
+      uint32_t x[4];
+      bool ragged = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
       {
-        const int it = seg0 + j;
-        if (fillIt < itersAll)
-          cp_async16(mySlot + ((it + STAGES - 1) % STAGES) * ringThreads, fillPtr);
-        cp_async_commit();
-        ++fillIt;
-        fillPtr += rowStep;
-        cp_async_wait<STAGES - 1>();
-        const uint4 cur = mySlot[(it % STAGES) * ringThreads];
-        const uint32_t wd[4] = {cur.x, cur.y, cur.z, cur.w};
-        uint32_t fl[4];
-        bool ragged = false;
+        const uint32_t ci = __byte_perm(wd[k], 0u, 0x4431);                    // U | V << 8
+        uint32_t lo, nhi;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(lo) : "r"(tbl + ci));
+        asm volatile("ld.shared.u8 %0, [%1+65536];" : "=r"(nhi) : "r"(tbl + ci));
+        x[k] = lut_pass_pair(wd[k], lo, nhi);
+        ragged |= (lo * 256u + nhi == LUT_RAGGED_CODE);
+      }
+      if (__any_sync(__activemask(), ragged))
+      {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
         {
-          const uint32_t e = s_table[__byte_perm(wd[k], 0u, 0x4431)];          // U | V << 8
-          fl[k] = lut_fail_pair(wd[k], e);
-          ragged |= (e == LUT_RAGGED);
+          const uint32_t ci = __byte_perm(wd[k], 0u, 0x4431);
+          if (s_table[ci] == LUT_RAGGED_LO && s_table[65536u + ci] == LUT_RAGGED_NHI)
+            x[k] = lut_pass_pair_masks(wd[k], ci, masks);
         }
-        if (__any_sync(__activemask(), ragged))
-        {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-          {
-            const uint32_t ci = __byte_perm(wd[k], 0u, 0x4431);
-            if (s_table[ci] == LUT_RAGGED)
-            {
-              const uint32_t y0 = wd[k] & 0xFFu, y1 = (wd[k] >> 16) & 0xFFu;
-              const uint32_t m0 = __ldg(masks + (size_t)ci * 8u + (y0 >> 5));
-              const uint32_t m1 = __ldg(masks + (size_t)ci * 8u + (y1 >> 5));
-              const uint32_t pass = ((m0 >> (y0 & 31u)) & 1u) | (((m1 >> (y1 & 31u)) & 1u) << 16);
-              fl[k] = 0x00010001u - pass;                                    // the interval test said "fail, fail"
-            }
-          }
-        }
-        const uint32_t Sc = (fl[0] + fl[1]) + (fl[2] + fl[3]);
-        A  += fl[1] + 2u * fl[2] + 3u * fl[3];
-        S  += Sc;
-        SI += (uint32_t)j * Sc;
       }
-      const uint32_t segFails = (S & 0xFFFFu) + (S >> 16);
-      fails  += segFails;
+      // pass lanes {0,1} are x >> 15; the shifts and all sums ride on IMAD.HI (x * 2^17 >> 32)
+      uint32_t Pc = __umulhi(x[0], 1u << 17);
+      Pc = __umulhi(x[1], 1u << 17) + Pc;
+      Pc = __umulhi(x[2], 1u << 17) + Pc;
+      Pc = __umulhi(x[3], 1u << 17) + Pc;
+      A = __umulhi(x[1], 1u << 17) + A;
+      A = __umulhi(x[2], 2u << 17) + A;
+      A = __umulhi(x[3], 3u << 17) + A;
+      S += Pc;
+      SI += j * Pc;
+    };
+    // packed lane sums are flushed every 128 iterations (SI <= 4 * 127 * 128 / 2 < 2^16)
+    for (int seg0 = 0; seg0 < itersAll; seg0 += 128)
+    {
+      const int segN = min(128, itersAll - seg0);
+      int j = 0;
+      for (; j + STAGES <= segN; j += STAGES)
+      {
+#pragma unroll
+        for (int k = 0; k < STAGES; ++k)
+          body((uint32_t)k, (uint32_t)(j + k));          // seg0 and j are multiples of STAGES (128 % STAGES == 0)
+      }
+      for (; j < segN; ++j)
+        body((uint32_t)j % STAGES, (uint32_t)j);
+      const uint32_t segPasses = (S & 0xFFFFu) + (S >> 16);
+      passes += segPasses;
       inIdx  += 2u * ((A & 0xFFFFu) + (A >> 16)) + (S >> 16);
-      syFail += segFails * (uint32_t)(rr + seg0 * rpi) + (uint32_t)rpi * ((SI & 0xFFFFu) + (SI >> 16));
+      syPass += segPasses * (uint32_t)(rr + seg0 * rpi) + (uint32_t)rpi * ((SI & 0xFFFFu) + (SI >> 16));
+      S = 0u; A = 0u; SI = 0u;
     }
-    uint32_t sxFail = fails * ((uint32_t)cc * 8u) + inIdx;
+    uint32_t sxPass = passes * ((uint32_t)cc * 8u) + inIdx;
 
     // group reduction
     const unsigned am = __activemask();
-    fails  = __reduce_add_sync(am, fails);
-    sxFail = __reduce_add_sync(am, sxFail);
-    syFail = __reduce_add_sync(am, syFail);
+    passes = __reduce_add_sync(am, passes);
+    sxPass = __reduce_add_sync(am, sxPass);
+    syPass = __reduce_add_sync(am, syPass);
     if (lane == 0)
     {
-      myRed[warpInGroup * 4 + 0] = fails; myRed[warpInGroup * 4 + 1] = sxFail; myRed[warpInGroup * 4 + 2] = syFail;
+      myRed[warpInGroup * 4 + 0] = passes; myRed[warpInGroup * 4 + 1] = sxPass; myRed[warpInGroup * 4 + 2] = syPass;
     }
     group_barrier(1 + group, gthreads);
     if (warpInGroup == 0)
@@ -240,8 +270,8 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
       a = __reduce_add_sync(0xFFFFFFFFu, a);
       b = __reduce_add_sync(0xFFFFFFFFu, b);
       c = __reduce_add_sync(0xFFFFFFFFu, c);
-      if (lane == 0)
-        finalize_sum<KIND_WO>(g, p, a, b, c, 0u, out + frame, out);
+      if (lane == 0)      // finalize_sum works from the FAILING pixels' sums (all arithmetic modulo 2^32, as there)
+        finalize_sum<KIND_WO>(g, p, W * H - a, H * (W * (W - 1u) / 2u) - b, W * (H * (H - 1u) / 2u) - c, 0u, out + frame, out);
     }
     group_barrier(1 + group, gthreads);                  // myRed is reused by the next frame
   }
@@ -252,7 +282,7 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 lut_check_kernel(const uint32_t from, const uint32_t to, const uint32_t expected,
-                 const uint16_t* __restrict__ table, const uint32_t* __restrict__ masks,
+                 const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks,
                  unsigned long long* __restrict__ stats)     // [0] mismatching pixels, [1] never, [2] interval, [3] ragged entries, [4] passing pixels
 {
   __shared__ HueLutEntry s_lutHue[256];
@@ -268,23 +298,19 @@ lut_check_kernel(const uint32_t from, const uint32_t to, const uint32_t expected
   const uint32_t word = y0 | (u << 8) | ((y0 + 1u) << 16) | (v << 24);
   const uint32_t det = detect_pair_bits(word & 0x00FF00FFu, word, coef_yuyv(), s_lutHue, s_lut255, bd, expected);
   const uint32_t ci = __byte_perm(word, 0u, 0x4431);
-  const uint32_t e = table[ci];
-  uint32_t fl = lut_fail_pair(word, e);
-  if (e == LUT_RAGGED)
-  {
-    const uint32_t y1 = y0 + 1u;
-    const uint32_t m0 = masks[(size_t)ci * 8u + (y0 >> 5)], m1 = masks[(size_t)ci * 8u + (y1 >> 5)];
-    fl = 0x00010001u - (((m0 >> (y0 & 31u)) & 1u) | (((m1 >> (y1 & 31u)) & 1u) << 16));
-  }
-  const uint32_t passLut = ((fl & 1u) ^ 1u) | ((((fl >> 16) & 1u) ^ 1u) << 1);
+  const uint32_t lo = table[ci], nhi = table[65536u + ci];
+  const bool isRagged = lo == LUT_RAGGED_LO && nhi == LUT_RAGGED_NHI;
+  const bool isNever = lo == LUT_NEVER_LO && nhi == LUT_NEVER_NHI;
+  const uint32_t x = isRagged ? lut_pass_pair_masks(word, ci, masks) : lut_pass_pair(word, lo, nhi);
+  const uint32_t passLut = ((x >> 15) & 1u) | ((x >> 31) << 1);
   const uint32_t bad = (uint32_t)__popc(passLut ^ det);
   if (bad) atomicAdd(stats + 0, (unsigned long long)bad);
   if (det) atomicAdd(stats + 4, (unsigned long long)__popc(det));
   if ((i & 127u) == 0u)
-    atomicAdd(stats + (e == LUT_NEVER ? 1 : (e == LUT_RAGGED ? 3 : 2)), 1ull);
+    atomicAdd(stats + (isNever ? 1 : (isRagged ? 3 : 2)), 1ull);
 }
 
-cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, const uint16_t* table, const uint32_t* masks,
+cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, const uint8_t* table, const uint32_t* masks,
                              unsigned long long* stats, cudaStream_t stream)
 {
   lut_check_kernel<<<(1u << 23) / 256, 256, 0, stream>>>(from, to, expected, table, masks, stats);
@@ -293,7 +319,7 @@ cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, cons
 }
 
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
-                          const uint16_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream)
+                          const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream)
 {
   if (numFrames <= 0)
     return cudaSuccess;
