@@ -78,3 +78,27 @@ def test_table_is_reused_and_rebuilt():
     n3 = lib().trikb200_launchCount()
     assert (n1 - n0, n2 - n1, n3 - n2) == (2, 1, 2)            # build + pass, pass, build + pass
     codec.close()
+
+
+OBJ_ARGS = [(1, 0, 20, 80, 20, 50, 30, 0), (1, 120, 25, 60, 35, 55, 40, 0), (1, 0, 40, 60, 40, 60, 40, 0), (1, 230, 30, 70, 30, 50, 40, 0)]
+
+
+@pytest.mark.parametrize("size", [(320, 240), (640, 480), (160, 120), (32, 8), (1280, 720)])
+def test_oo_bitmap_through_table_matches_oracle(size):
+    """OO with step 1 (threshold -> metapixel bitmap) through the table, one threshold set per batch."""
+    w, h = size
+    fams = [("noise", s) for s in range(3)] + [("scene", s) for s in range(3)] + [("blobs", s) for s in range(4)] + [(e, 0) for e in synth.EDGE_CASES]
+    if w < 64:
+        fams = [("noise", s) for s in range(4)] + [("zero", 0), ("red", 0)]
+    frames = np.stack([synth.make_frame(f, s, w, h, "yuv422p") for f, s in fams])
+    codec = open_sensor("oo", w, h)
+    for args in OBJ_ARGS:
+        orc = oracle.OracleSensor("oo", w, h)
+        want = [bytes(memoryview(orc.process(frames[i], oracle.ObjInArgs(*args))[1]))[:24] for i in range(len(fams))]
+        for mode in (1, -1):
+            lib().trikb200_setLutMode(mode)
+            ret, outs = codec.process_batch(frames, xdm.ObjInArgsAlg(*args))
+            assert ret == 0, lib().trikb200_lastError()
+            got = [bytes(memoryview(o))[:24] for o in outs]
+            assert got == want, (size, args, mode, [i for i in range(len(got)) if got[i] != want[i]][:8])
+    codec.close()

@@ -404,6 +404,24 @@ void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, const uin
   }
 }
 
+// build (or keep) the chroma table of a threshold set on stream s
+bool ensure_lut(Instance* in, const FrameParams& fp, bool have, cudaStream_t s)
+{
+  if (have)
+    return true;
+  if (!in->dLutTable)
+  {
+    CUDA_TRY(cudaMalloc(&in->dLutTable, LUT_TABLE_BYTES));
+    CUDA_TRY(cudaMalloc(&in->dLutMasks, LUT_MASK_BYTES));
+    CUDA_TRY(cudaDeviceGetAttribute(&in->smCount, cudaDevAttrMultiProcessorCount, in->device));
+  }
+  in->lutValid = false;
+  CUDA_TRY(launch_chroma_table(fp.from, fp.to, fp.expected, in->dLutTable, in->dLutMasks, s));
+  in->lutFrom = fp.from; in->lutTo = fp.to; in->lutExpected = fp.expected;
+  in->lutValid = true; in->lutStream = s;
+  return true;
+}
+
 bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
 {
   if (!in->valid || in->geo.width <= 0 || in->geo.height <= 0)
@@ -550,18 +568,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
         const bool have = in->lutValid && in->lutStream == s && in->lutFrom == fp.from && in->lutTo == fp.to
                           && in->lutExpected == fp.expected;
         useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32);
-        if (useLut && !have)
-        {
-          if (!in->dLutTable)
-          {
-            CUDA_TRY(cudaMalloc(&in->dLutTable, LUT_TABLE_BYTES));
-            CUDA_TRY(cudaMalloc(&in->dLutMasks, LUT_MASK_BYTES));
-            CUDA_TRY(cudaDeviceGetAttribute(&in->smCount, cudaDevAttrMultiProcessorCount, in->device));
-          }
-          CUDA_TRY(launch_chroma_table(fp.from, fp.to, fp.expected, in->dLutTable, in->dLutMasks, s));
-          in->lutFrom = fp.from; in->lutTo = fp.to; in->lutExpected = fp.expected;
-          in->lutValid = true; in->lutStream = s;
-        }
+        if (useLut && !ensure_lut(in, fp, have, s)) return false;
       }
       if (useLut)
         CUDA_TRY(launch_wo_lut(g, b.n, dFrames, in->dParams, in->dLutTable, in->dLutMasks,
@@ -586,7 +593,21 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       if (!in->grow_device(in->dBitmaps, in->dBitmapsCap, cells * b.n, false)) return false;
       if (!in->grow_device(in->dClusters, in->dClustersCap, (size_t)12 * maxLabels * b.n, false)) return false;
       if (!in->grow_device(in->dEqual, in->dEqualCap, (size_t)maxLabels * b.n, false)) return false;
-      CUDA_TRY(launch_oo(g, b.n, dFrames, in->dParams, pstride, in->dBitmaps, in->dClusters, in->dEqual, maxLabels, dOut, nullptr, s));
+      // all frames under one threshold set (the usual case: the range is carried state): step 1 through the chroma table
+      bool useLut = g_lutMode >= 0;
+      const FrameParams& fp0 = in->paramsScratch[0];
+      for (size_t i = 1; useLut && i < np; ++i)
+        useLut = in->paramsScratch[i].from == fp0.from && in->paramsScratch[i].to == fp0.to
+                 && in->paramsScratch[i].expected == fp0.expected;
+      if (useLut)
+      {
+        const bool have = in->lutValid && in->lutStream == s && in->lutFrom == fp0.from && in->lutTo == fp0.to
+                          && in->lutExpected == fp0.expected;
+        useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32);
+        if (useLut && !ensure_lut(in, fp0, have, s)) return false;
+      }
+      CUDA_TRY(launch_oo(g, b.n, dFrames, in->dParams, pstride, in->dBitmaps, in->dClusters, in->dEqual, maxLabels, dOut, nullptr, s,
+                         useLut ? in->dLutTable : nullptr, in->dLutMasks, in->smCount));
       break;
     }
     default:

@@ -72,9 +72,11 @@ cudaError_t launch_om(const Geometry& g, int numFrames, const uint8_t* frames, c
                       cudaStream_t stream);
 // OO: bitmaps = numFrames x (W/4)(H/4) uint16; clusters = numFrames x maxLabels x 12 bytes;
 // equal = numFrames x maxLabels uint16; out = numFrames x 36-byte ObjOutArgsAlg records
+// lutTable != nullptr: all frames share one threshold set and step 1 goes through its chroma table
 cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                       int paramStride, uint16_t* bitmaps, void* clusters, uint16_t* equal, int maxLabels,
-                      void* out, int* labelCounts, cudaStream_t stream);
+                      void* out, int* labelCounts, cudaStream_t stream,
+                      const uint8_t* lutTable = nullptr, const uint32_t* lutMasks = nullptr, int smCount = 0);
 inline int oo_max_labels(int width, int height) { return ((width / 4) / 2 + 1) * ((height / 4) / 2 + 1) + 2; }
 
 // auto-calibration histograms over the frames listed in frameIdx (device array of numFlagged indices)
@@ -106,6 +108,8 @@ constexpr size_t LUT_TABLE_BYTES = 2 * 65536;
 constexpr size_t LUT_MASK_BYTES  = (size_t)65536 * 8 * sizeof(uint32_t);
 cudaError_t launch_chroma_table(uint32_t from, uint32_t to, uint32_t expected, uint8_t* table, uint32_t* masks,
                                 cudaStream_t stream);
+cudaError_t launch_oo_bitmap_lut(const Geometry& g, int numFrames, const uint8_t* frames, const uint8_t* table,
+                                 const uint32_t* masks, uint16_t* bitmaps, int smCount, cudaStream_t stream);
 cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, const uint8_t* table, const uint32_t* masks,
                              unsigned long long* stats, cudaStream_t stream);
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,

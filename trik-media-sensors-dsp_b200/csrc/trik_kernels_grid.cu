@@ -625,13 +625,15 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
 
 cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                       int paramStride, uint16_t* bitmaps, void* clusters, uint16_t* equal, int maxLabels,
-                      void* out, int* labelCounts, cudaStream_t stream)
+                      void* out, int* labelCounts, cudaStream_t stream,
+                      const uint8_t* lutTable, const uint32_t* lutMasks, int smCount)
 {
   if (numFrames <= 0)
     return cudaSuccess;
   const int cpr = g.width / 16;
   if (cpr <= 0 || cpr > 1024)
     return cudaErrorInvalidValue;
+  const bool viaTable = lutTable != nullptr && cpr <= 768;
   const int k = rows_per_iteration(cpr, 192);
   const int bh = g.height / 4;
   int slabs = (148 * 8 + numFrames - 1) / numFrames;
@@ -640,9 +642,15 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
   if (slabs < 1) slabs = 1;
   if (slabs > 65535) slabs = 65535;
   dim3 grid((unsigned)numFrames, (unsigned)slabs);
-  oo_bitmap_kernel<<<grid, cpr * k, 0, stream>>>(g, frames, params, paramStride, bitmaps, cpr, k);
-  ++g_launches_grid;
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (viaTable)
+    e = launch_oo_bitmap_lut(g, numFrames, frames, lutTable, lutMasks, bitmaps, smCount, stream);
+  else
+  {
+    oo_bitmap_kernel<<<grid, cpr * k, 0, stream>>>(g, frames, params, paramStride, bitmaps, cpr, k);
+    ++g_launches_grid;
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess)
     return e;
   const size_t rowBytes = (size_t)2 * (g.width / 4) * sizeof(uint16_t);

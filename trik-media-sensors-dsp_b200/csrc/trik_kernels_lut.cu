@@ -278,6 +278,112 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
 }
 
 // ---------------------------------------------------------------------------------------------
+// OO step 1 through the table: threshold -> metapixel bitmap (cv_bitmap_builder_reference.hpp:163-187)
+// ---------------------------------------------------------------------------------------------
+// bitmap[(row/4) * (W/4) + col/4], bit (row%4)*4 + col%4 = det.  A thread produces the four metapixels under one
+// 16-pixel luma chunk: 4 rows x (16 luma + 16 chroma bytes), one 8-byte store.  Persistent CTAs (table in shared
+// memory, one per SM), blockDim = cpr * rows: `rows` metapixel rows of the batch at a time, no barrier needed.
+__global__ void __launch_bounds__(768, 1)
+oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ table,
+                     const uint32_t* __restrict__ masks, uint16_t* __restrict__ bitmaps,
+                     const int numFrames, const int cpr, const int rows)
+{
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(table);
+    uint4* dst = reinterpret_cast<uint4*>(s_raw);
+    for (int i = threadIdx.x; i < 131072 / 16; i += blockDim.x)
+      dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= cpr * rows)
+    return;
+  const int cc = t % cpr, rr = t / cpr;
+  const int bw = g.width / 4, bh = g.height / 4;
+  const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(s_raw);
+  const size_t chromaOfs = (size_t)g.height * g.lineLength;
+  const long long units = (long long)numFrames * bh;                 // (frame, metapixel row)
+
+  for (long long u = (long long)blockIdx.x * rows + rr; u < units; u += (long long)gridDim.x * rows)
+  {
+    const int frame = (int)(u / bh);
+    const int mr = (int)(u - (long long)frame * bh);
+    const uint8_t* ptr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)(mr * 4) * g.lineLength;
+    uint4 lu[4], ch[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+      lu[r] = ld_stream(ptr + (size_t)r * g.lineLength);
+      ch[r] = ld_stream(ptr + (size_t)r * g.lineLength + chromaOfs);
+    }
+    uint32_t meta[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+      const uint32_t L[4] = {lu[r].x, lu[r].y, lu[r].z, lu[r].w};
+      const uint32_t Cw[4] = {ch[r].x, ch[r].y, ch[r].z, ch[r].w};
+      uint32_t x[8];
+      bool ragged = false;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        const uint32_t yy = __byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140);     // Y0 | Y1 << 16
+        const uint32_t ci = __byte_perm(Cw[k >> 1], 0u, (k & 1) ? 0x4423 : 0x4401);    // U | V << 8 (plane bytes: V U V U)
+        uint32_t lo, nhi;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(lo) : "r"(tbl + ci));
+        asm volatile("ld.shared.u8 %0, [%1+65536];" : "=r"(nhi) : "r"(tbl + ci));
+        x[k] = lut_pass_pair(yy, lo, nhi);
+        ragged |= (lo * 256u + nhi == LUT_RAGGED_CODE);
+      }
+      if (__any_sync(__activemask(), ragged))
+      {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+          const uint32_t ci = __byte_perm(Cw[k >> 1], 0u, (k & 1) ? 0x4423 : 0x4401);
+          if (s_raw[ci] == LUT_RAGGED_LO && s_raw[65536u + ci] == LUT_RAGGED_NHI)
+            x[k] = lut_pass_pair_masks(__byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140), ci, masks);
+        }
+      }
+      // bit 15 -> bit s, bit 31 -> bit s + 1 (s = 4r + 2(k&1) <= 14) in ONE IMAD.HI: with M = 2^(17+s) + 2^(s+2),
+      // (x * M) >> 32 = a 2^s + b 2^(s+1) + b 2^(16+s) for x = a 2^15 + b 2^31; the stray bit is masked at the end
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        const int sft = r * 4 + (k & 1) * 2;
+        meta[k >> 1] = __umulhi(x[k], (1u << (17 + sft)) + (1u << (sft + 2))) + meta[k >> 1];
+      }
+    }
+    uint2 v;
+    v.x = (meta[0] & 0xFFFFu) | (meta[1] << 16);
+    v.y = (meta[2] & 0xFFFFu) | (meta[3] << 16);
+    *reinterpret_cast<uint2*>(bitmaps + ((size_t)frame * bh + mr) * bw + cc * 4) = v;
+  }
+}
+
+cudaError_t launch_oo_bitmap_lut(const Geometry& g, int numFrames, const uint8_t* frames, const uint8_t* table,
+                                 const uint32_t* masks, uint16_t* bitmaps, int smCount, cudaStream_t stream)
+{
+  if (numFrames <= 0)
+    return cudaSuccess;
+  const int cpr = g.width / 16;
+  if (cpr <= 0 || cpr > 768)
+    return cudaErrorInvalidValue;
+  const int rows = 768 / cpr;
+  const int threads = ((cpr * rows + 31) / 32) * 32;
+  const long long units = (long long)numFrames * (g.height / 4);
+  long long grid = (units + rows - 1) / rows;
+  if (grid > smCount) grid = smCount;
+  cudaError_t e = cudaFuncSetAttribute(oo_bitmap_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+  if (e != cudaSuccess)
+    return e;
+  oo_bitmap_lut_kernel<<<(unsigned)grid, threads, 131072, stream>>>(g, frames, table, masks, bitmaps, numFrames, cpr, rows);
+  ++g_launches_lut;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // self-check used by the parity tests: table-based detection against the arithmetic on all 2^24 inputs
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
