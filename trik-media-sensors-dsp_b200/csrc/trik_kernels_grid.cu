@@ -16,6 +16,7 @@
 //     pixel of a label is not counted, merge in label order, std::sort tie order), so it is
 //     replayed step for step by one lane per frame; frames run in parallel.
 #include <atomic>
+#include <cstdlib>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 
@@ -419,14 +420,20 @@ static_assert(sizeof(ObjOut) == 36, "ObjOutArgsAlg layout");
 // One warp per frame.  The 32 lanes test 32 metapixels at a time (popcount > 2) and vote; lane 0 then
 // walks only the set bits in raster order and replays the reference's labelling on them.  The label
 // tables live in shared memory when they fit (tablesInSmem), else in the global scratch.
-__global__ void __launch_bounds__(32)
+// One warp per frame, OO_WARPS_PER_CTA independent warps per CTA (they share nothing but the launch): the walk is
+// a chain of dependent shuffles and small table updates, so what hides its latency is the number of resident warps.
+constexpr int OO_WARPS_PER_CTA = 2;
+__global__ void __launch_bounds__(32 * OO_WARPS_PER_CTA)
 oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoCluster* __restrict__ clustersAll,
                   uint16_t* __restrict__ equalAll, const int maxLabels, const int tablesInSmem,
-                  ObjOut* __restrict__ out, int* __restrict__ labelCounts)
+                  ObjOut* __restrict__ out, int* __restrict__ labelCounts, const int numFrames, const int smemPerWarp)
 {
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  const int frame = blockIdx.x;
-  const int lane = threadIdx.x;
+  extern __shared__ __align__(16) uint8_t s_all[];
+  const int frame = blockIdx.x * OO_WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (frame >= numFrames)
+    return;
+  uint8_t* const s_raw = s_all + (size_t)(threadIdx.x >> 5) * smemPerWarp;
+  const int lane = threadIdx.x & 31;
   const int bw = g.width / 4, bh = g.height / 4;
   const uint16_t* bm = bitmaps + (size_t)frame * bw * bh;
   // shared layout: [clusters (12 B each)] [equal (2 B each)] [two label rows of bw+? u16]
@@ -655,12 +662,18 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
     return e;
   const size_t rowBytes = (size_t)2 * (g.width / 4) * sizeof(uint16_t);
   const size_t tableBytes = (size_t)maxLabels * sizeof(OoCluster) + (size_t)((maxLabels + 7) & ~7) * sizeof(uint16_t);
-  const int tablesInSmem = (tableBytes + rowBytes <= 200 * 1024) ? 1 : 0;
-  const size_t smem = rowBytes + (tablesInSmem ? tableBytes : 0);
+  // one warp per frame: residency is what hides its latency, so the tables only live in shared memory while
+  // that still leaves ~10 CTAs per SM (env override for A/B measurements)
+  static const long smemLimit = getenv("TRIKB200_OO_SMEM_LIMIT") ? atol(getenv("TRIKB200_OO_SMEM_LIMIT")) : 4 * 1024;
+  const int tablesInSmem = ((long)(tableBytes + rowBytes) <= smemLimit) ? 1 : 0;
+  const size_t smemPerWarp = ((rowBytes + (tablesInSmem ? tableBytes : 0)) + 15) & ~(size_t)15;
+  const size_t smem = smemPerWarp * OO_WARPS_PER_CTA;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(oo_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  oo_cluster_kernel<<<(unsigned)numFrames, 32, smem, stream>>>(g, bitmaps, reinterpret_cast<OoCluster*>(clusters), equal,
-                                                               maxLabels, tablesInSmem, reinterpret_cast<ObjOut*>(out), labelCounts);
+  const unsigned ctas = (unsigned)((numFrames + OO_WARPS_PER_CTA - 1) / OO_WARPS_PER_CTA);
+  oo_cluster_kernel<<<ctas, 32 * OO_WARPS_PER_CTA, smem, stream>>>(g, bitmaps, reinterpret_cast<OoCluster*>(clusters), equal,
+                                                                   maxLabels, tablesInSmem, reinterpret_cast<ObjOut*>(out), labelCounts,
+                                                                   numFrames, (int)smemPerWarp);
   ++g_launches_grid;
   return cudaGetLastError();
 }
