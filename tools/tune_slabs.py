@@ -31,6 +31,7 @@ SLABS = [int(x) for x in os.environ.get("SLABS", "0").split(",")]
 STAGES = [int(x) for x in os.environ.get("STAGES", "-1,100,102,104,200,202,204").split(",")]
 THREADS = [int(x) for x in os.environ.get("THREADS", "0").split(",")]
 lib().trikb200_setOverlapLaunch(int(os.environ.get("OVERLAP", "1")))
+lib().trikb200_setFramesPerCta(int(os.environ.get("FPC", "0")))
 ref_out = None
 for stages, slabs, threads in [(a, b, c) for a in STAGES for b in SLABS for c in THREADS]:
     lib().trikb200_setBlockThreads(threads)
@@ -57,5 +58,5 @@ for stages, slabs, threads in [(a, b, c) for a in STAGES for b in SLABS for c in
     if ref_out is None:
         ref_out = cur
     assert cur == ref_out, "results changed with the tuning knobs"
-    print(json.dumps({"sensor": kind, "size": "%dx%d" % (w, h), "batch": n, "slabs": slabs, "stages": stages, "threads": threads, "overlap": int(os.environ.get("OVERLAP", "1")), "ms": best,
+    print(json.dumps({"sensor": kind, "size": "%dx%d" % (w, h), "batch": n, "slabs": slabs, "stages": stages, "threads": threads, "overlap": int(os.environ.get("OVERLAP", "1")), "fpc": int(os.environ.get("FPC", "0")), "ms": best,
                       "GBps": n * w * h * 2 / best / 1e6}), flush=True)

@@ -1363,6 +1363,7 @@ void trikb200_setLoadStages(XDAS_Int32 stages) { set_sum_stages(stages); }
 void trikb200_setBlockThreads(XDAS_Int32 threads) { set_target_threads(threads); }
 void trikb200_setOverlapLaunch(XDAS_Int32 on) { set_overlap_launch(on); }
 void trikb200_setLutMode(XDAS_Int32 mode) { g_lutMode = mode; }
+void trikb200_setFramesPerCta(XDAS_Int32 n) { set_frames_per_cta(n); }
 const char* trikb200_lastError(void) { return t_lastError.c_str(); }
 
 /* test probes: exhaustive pixel functions straight from the device code (tests/test_pixel_gpu.py) */

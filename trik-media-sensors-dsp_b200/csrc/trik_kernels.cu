@@ -28,6 +28,8 @@ static std::atomic<long long> g_launches{0};
 //   v / 100 = 0 per-sensor default kernel, 1 force the first-version kernel, 2 force the tuned line kernel.
 static int g_targetThreads = 0;             // 0 = default (about 256 threads per CTA)
 void set_target_threads(int t) { g_targetThreads = t; }
+static int g_framesPerCta = 0;               // wide OL kernel: 0 = heuristic, 1 = off, n = force
+void set_frames_per_cta(int n) { g_framesPerCta = n; }
 static int g_overlapLaunch = 1;              // programmatic dependent launch of the tuned line kernel
 void set_overlap_launch(int on) { g_overlapLaunch = on ? 1 : 0; }
 static int g_tuneStages = -1;
@@ -563,26 +565,37 @@ template <int STAGES, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 vsum16_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
               const int paramStride, SumAcc* __restrict__ acc, TargetOut* __restrict__ out,
-              const int slabs, const int rowsPerSlab, const int cpr, const int rpi)
+              const int slabs, const int rowsPerSlab, const int cpr, const int rpiAll,
+              const int framesPerCta, const int numFrames)
 {
   static_assert(STAGES >= 2, "ring depth");
   __shared__ uint32_t s_red[32][4];
+  __shared__ uint32_t s_sums[8][4];            // framesPerCta > 1: per-frame totals by shared atomics
   extern __shared__ uint4 s_ring[];            // [STAGES][2][blockDim]: luma chunk, chroma chunk
 
   asm volatile("griddepcontrol.launch_dependents;");
-  const int frame = blockIdx.x / slabs;
-  const int slab  = blockIdx.x - frame * slabs;
+  // framesPerCta == 1: a CTA is one slab of one frame.  framesPerCta == F > 1 (then slabs == 1): the rows of one
+  // iteration are dealt out to F frames, so a thread walks its frame with a stride of rpiAll / F rows and gets
+  // F x the iterations to spread its prologue and epilogue over (what small frames lack).
   const int t  = threadIdx.x;
   const int cc = t % cpr;
-  const int rr = t / cpr;
+  const int rrAll = t / cpr;
+  const int rpi = rpiAll / framesPerCta;
+  const int sub = rrAll / rpi;                 // which of this CTA's frames
+  const int rr = rrAll - sub * rpi;
+  const int frame = framesPerCta > 1 ? (int)blockIdx.x * framesPerCta + sub : (int)blockIdx.x / slabs;
+  const int slab  = framesPerCta > 1 ? 0 : (int)blockIdx.x - frame * slabs;
+  const bool live = frame < numFrames;
+  if (framesPerCta > 1 && t < 32)
+    s_sums[t >> 2][t & 3] = 0u;
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const FrameParams p = params[(size_t)frame * paramStride];
+  const FrameParams p = params[live ? (size_t)frame * paramStride : 0];
 
   const int r0 = slab * rowsPerSlab;
   const int r1 = min(r0 + rowsPerSlab, g.height);
   const int firstRow = r0 + rr;
-  const int iters = firstRow < r1 ? (r1 - firstRow + rpi - 1) / rpi : 0;
-  const uint8_t* fillPtr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)firstRow * g.lineLength;
+  const int iters = (live && firstRow < r1) ? (r1 - firstRow + rpi - 1) / rpi : 0;
+  const uint8_t* fillPtr = frames + (size_t)(live ? frame : 0) * g.frameStride + (size_t)cc * 16u + (size_t)firstRow * g.lineLength;
   const size_t rowStep = (size_t)rpi * g.lineLength;
   const size_t chromaOfs = (size_t)g.height * g.lineLength;
 
@@ -685,6 +698,24 @@ vsum16_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   const uint32_t bandBias2 = (((uint32_t)(itB - itA) * 8u * nLane) & 0xFFFFu) * 0x10001u;
   uint32_t crossFail = lanes_total(lanes_sub(lanes_sub(snapB, snapA), bandBias2));
 
+  if (framesPerCta > 1)
+  {
+    __syncthreads();                                     // s_sums zeroed
+    if (live)
+    {
+      atomicAdd(&s_sums[sub][0], fails);
+      atomicAdd(&s_sums[sub][1], sxFail);
+      atomicAdd(&s_sums[sub][3], crossFail);
+    }
+    __syncthreads();
+    if (t < framesPerCta && (int)blockIdx.x * framesPerCta + t < numFrames)
+    {
+      const int f = (int)blockIdx.x * framesPerCta + t;
+      const FrameParams pf = params[(size_t)f * paramStride];
+      finalize_sum<KIND_OL>(g, pf, s_sums[t][0], s_sums[t][1], 0u, s_sums[t][3], out + f, out);
+    }
+    return;
+  }
   __syncthreads();
   const unsigned am = __activemask();
   fails  = __reduce_add_sync(am, fails);
@@ -846,19 +877,28 @@ cudaError_t launch_sum_sensor(int kind, const Geometry& g, int numFrames, const 
     case KIND_OL:
       if (g_widePlanarKernel)
       {
+        // small frames: two frames per CTA, so that a thread has ~60 iterations to spread its prologue / epilogue over
+        int fpc = 1;
+        if (slabs == 1 && g_framesPerCta != 1)
+        {
+          const int itersOne = (g.height + rpi - 1) / rpi;
+          const int want = g_framesPerCta > 1 ? g_framesPerCta : (itersOne >= 50 ? 1 : 2);     // measured: 2 gives +2 % at 320x240, 4 loses 6 %
+          for (fpc = want > 8 ? 8 : want; fpc > 1 && (rpi % fpc != 0 || g.height % (rpi / fpc) != 0); --fpc) {}
+        }
+        const long long gridW = fpc > 1 ? (numFrames + fpc - 1) / fpc : grid;
 #define TRIK_LAUNCH_W2(ST, MT, MB)                                                                                       \
   do {                                                                                                           \
     if (ringBytes > 48 * 1024)                                                                                   \
       cudaFuncSetAttribute(vsum16_kernel<ST, MT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);  \
     cudaLaunchConfig_t cfg = {};                                                                                 \
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads);                                  \
+    cfg.gridDim = dim3((unsigned)gridW); cfg.blockDim = dim3((unsigned)threads);                                 \
     cfg.dynamicSmemBytes = ringBytes; cfg.stream = stream;                                                       \
     cudaLaunchAttribute attr[1];                                                                                 \
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                             \
     attr[0].val.programmaticStreamSerializationAllowed = 1;                                                      \
     cfg.attrs = attr; cfg.numAttrs = g_overlapLaunch ? 1u : 0u;                                                  \
     cudaLaunchKernelEx(&cfg, vsum16_kernel<ST, MT, MB>, g, frames, params, paramStride, acc, out, slabs, rowsPerSlab,\
-                       cpr, rpi);                                                                                \
+                       cpr, rpi, fpc, numFrames);                                                                \
   } while (0)
 #define TRIK_LAUNCH_W(ST, MB) do { if (threads <= 256) TRIK_LAUNCH_W2(ST, 256, MB); else TRIK_LAUNCH_W2(ST, 1024, 1); } while (0)
         switch (stages)

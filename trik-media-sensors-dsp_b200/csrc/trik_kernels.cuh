@@ -103,6 +103,7 @@ int sum_sensor_block_threads(int kind, int width);
 void set_sum_stages(int stages);
 void set_target_threads(int threads);
 void set_overlap_launch(int on);
+void set_frames_per_cta(int n);
 // chroma-indexed detection table (trik_kernels_lut.cu): 2 x 65 536 bytes + 65 536 x 8 x uint32
 constexpr size_t LUT_TABLE_BYTES = 2 * 65536;
 constexpr size_t LUT_MASK_BYTES  = (size_t)65536 * 8 * sizeof(uint32_t);
