@@ -188,6 +188,11 @@ void trikb200_delete(IVIDTRANSCODE_Handle handle);
                                    device or pinned host memory and no frame that needs the host
                                    annealing tail (autoDetectHsv on WL/OL/OO), else XDM_EFAIL */
 
+#define TRIKB200_BATCH_DEVICE_TAIL 2  /* run the annealing tail of autoDetectHsv (WL/OL/OO) on the device instead of the
+                                   host: lifts the TRIKB200_BATCH_ASYNC restriction above.  Same generator and
+                                   arithmetic; only pow() is the device's (<= 2 ulp) instead of libm's, see
+                                   DESIGN.md 3.6 for the measured agreement */
+
 typedef struct TRIKB200_Batch {
     XDAS_Int32  size;          /* sizeof(TRIKB200_Batch) */
     XDAS_Int32  numFrames;

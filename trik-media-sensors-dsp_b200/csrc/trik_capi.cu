@@ -142,6 +142,9 @@ struct Instance {
   FrameParams  dBroadcast = {};     bool dBroadcastValid = false;  cudaStream_t dBroadcastStream = nullptr;
   uint8_t*     hOut = nullptr;      size_t hOutCap = 0;
   int*         hFlagged = nullptr;  size_t hFlaggedCap = 0;
+  uint32_t*    hSeeds = nullptr;    size_t hSeedsCap = 0;      // device annealing tail: one seed per calibrating frame
+  uint32_t*    dSeeds = nullptr;    size_t dSeedsCap = 0;
+  cudaEvent_t  hStageFree = nullptr;                           // completes when hFlagged / hSeeds have been read
   int32_t*     hHist = nullptr;     size_t hHistCap = 0;
 
   ~Instance() { release(); }
@@ -171,6 +174,9 @@ struct Instance {
     cudaFreeHost(hOut);     hOut = nullptr;     hOutCap = 0;
     cudaFreeHost(hFlagged); hFlagged = nullptr; hFlaggedCap = 0;
     cudaFreeHost(hHist);    hHist = nullptr;    hHistCap = 0;
+    cudaFreeHost(hSeeds);   hSeeds = nullptr;   hSeedsCap = 0;
+    cudaFree(dSeeds); dSeeds = nullptr; dSeedsCap = 0;
+    if (hStageFree) { cudaEventDestroy(hStageFree); hStageFree = nullptr; }
   }
 
   void free_maps()
@@ -310,6 +316,7 @@ struct BatchView {
   const int64_t* seeds; bool seedsBroadcast;
   cudaStream_t   stream;
   bool           async;
+  bool           deviceTail = false;     // TRIKB200_BATCH_DEVICE_TAIL
   // scattered form (trikb200_processMixed): one pointer per frame instead of base + stride
   const int32_t* streamIds = nullptr; int numStreams = 0;
   uint8_t* previews = nullptr; int64_t previewStride = 0; bool previewsOnDevice = false;
@@ -384,11 +391,16 @@ void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, const uin
     {
       TRIKB200_ObjOutArgsAlg* o = reinterpret_cast<TRIKB200_ObjOutArgsAlg*>(dst);
       memcpy(o->target, rec, sizeof(o->target));           // memset + fill of all eight (cv_ball_detector_seqpass.hpp:569-597)
-      if (detect && wants_autodetect(kind, inArgsAlg))
+      if (wants_autodetect(kind, inArgsAlg))
       {
-        o->detectHue = detect[0]; o->detectHueTolerance = detect[1];
-        o->detectSat = detect[2]; o->detectSatTolerance = detect[3];
-        o->detectVal = detect[4]; o->detectValTolerance = detect[5];
+        if (detect)                                         // host annealing tail
+        {
+          o->detectHue = detect[0]; o->detectHueTolerance = detect[1];
+          o->detectSat = detect[2]; o->detectSatTolerance = detect[3];
+          o->detectVal = detect[4]; o->detectValTolerance = detect[5];
+        }
+        else                                                // device tail: the record carries them
+          memcpy(&o->detectHue, rec + sizeof(o->target), 6 * sizeof(uint16_t));
       }
       break;
     }
@@ -458,7 +470,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
     else if (wants_autodetect(kind, ia))
       numFlagged += b.broadcast_in() ? b.n : 1;
   }
-  const bool hostTail = numFlagged > 0 && kind != KIND_WO;
+  const bool hostTail = numFlagged > 0 && kind != KIND_WO && !b.deviceTail;
   if (hostTail && (b.async || b.outOnDevice))
   {
     set_error("annealed auto-detect needs its host tail: not available with TRIKB200_BATCH_ASYNC or device results");
@@ -619,6 +631,11 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
   const int histBins = (kind == KIND_OO) ? 1024 : 256;
   if (numFlagged > 0)
   {
+    // pinned staging of the frame list (and seeds): an earlier asynchronous batch may still be reading it
+    if (in->hStageFree)
+      CUDA_TRY(cudaEventSynchronize(in->hStageFree));
+    else
+      CUDA_TRY(cudaEventCreateWithFlags(&in->hStageFree, cudaEventDisableTiming));
     if (!in->grow_pinned(in->hFlagged, in->hFlaggedCap, (size_t)numFlagged)) return false;
     if (!in->grow_device(in->dFlagged, in->dFlaggedCap, (size_t)numFlagged, false)) return false;
     int k = 0;
@@ -626,6 +643,20 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       if (wants_autodetect(kind, b.in_args(i)))
         in->hFlagged[k++] = i;
     CUDA_TRY(cudaMemcpyAsync(in->dFlagged, in->hFlagged, sizeof(int) * numFlagged, cudaMemcpyHostToDevice, s));
+    const bool deviceTail = b.deviceTail && kind != KIND_WO;
+    if (deviceTail)
+    {
+      if (!in->grow_pinned(in->hSeeds, in->hSeedsCap, (size_t)numFlagged)) return false;
+      if (!in->grow_device(in->dSeeds, in->dSeedsCap, (size_t)numFlagged, false)) return false;
+      const unsigned now = (unsigned)time(NULL);                      // the reference's srand(time(NULL))
+      for (int j = 0; j < numFlagged; ++j)
+      {
+        const int64_t sd = b.seeds ? b.seeds[b.seedsBroadcast ? 0 : in->hFlagged[j]] : -1;
+        in->hSeeds[j] = sd >= 0 ? (uint32_t)sd : now;
+      }
+      CUDA_TRY(cudaMemcpyAsync(in->dSeeds, in->hSeeds, sizeof(uint32_t) * numFlagged, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaEventRecord(in->hStageFree, s));
     if (kind == KIND_WO)
       CUDA_TRY(launch_wo_detect(g, numFlagged, dFrames, in->dFlagged, reinterpret_cast<TargetOut*>(dOut), s));
     else
@@ -634,7 +665,10 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       if (!in->grow_device(in->dHist, in->dHistCap, words, false)) return false;
       if (!in->grow_pinned(in->hHist, in->hHistCap, words)) return false;
       CUDA_TRY(launch_ordered_hist(kind, g, numFlagged, dFrames, in->dFlagged, in->dHist, s));
-      CUDA_TRY(cudaMemcpyAsync(in->hHist, in->dHist, words * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (deviceTail)
+        CUDA_TRY(launch_anneal(kind, numFlagged, in->dFlagged, in->dHist, in->dSeeds, dOut, s));
+      else
+        CUDA_TRY(cudaMemcpyAsync(in->hHist, in->dHist, words * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
   }
 
@@ -1216,6 +1250,7 @@ XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Bat
   b.seeds = batch->seeds; b.seedsBroadcast = false;
   b.stream = reinterpret_cast<cudaStream_t>(batch->stream);
   b.async = (batch->flags & TRIKB200_BATCH_ASYNC) != 0;
+  b.deviceTail = (batch->flags & TRIKB200_BATCH_DEVICE_TAIL) != 0;
   if (batch->previews)
   {
     const long long need = (long long)in->outHeight * in->outLineLength;

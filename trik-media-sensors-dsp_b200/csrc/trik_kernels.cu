@@ -65,7 +65,8 @@ extern std::atomic<long long> g_launches_detect;
 extern std::atomic<long long> g_launches_preview;
 extern std::atomic<long long> g_launches_line;
 extern std::atomic<long long> g_launches_lut;
-long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line + g_launches_lut; }
+extern std::atomic<long long> g_launches_anneal;
+long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line + g_launches_lut + g_launches_anneal; }
 
 // ---------------------------------------------------------------------------------------------
 // per-pair work

@@ -103,6 +103,9 @@ int sum_sensor_block_threads(int kind, int width);
 void set_sum_stages(int stages);
 void set_target_threads(int threads);
 void set_overlap_launch(int on);
+// annealing tail of the WL / OL / OO auto-calibration on the device (trik_kernels_anneal.cu)
+cudaError_t launch_anneal(int kind, int numFlagged, const int* frameIdx, const int32_t* hist, const uint32_t* seeds,
+                          void* out, cudaStream_t stream);
 void set_frames_per_cta(int n);
 // chroma-indexed detection table (trik_kernels_lut.cu): 2 x 65 536 bytes + 65 536 x 8 x uint32
 constexpr size_t LUT_TABLE_BYTES = 2 * 65536;

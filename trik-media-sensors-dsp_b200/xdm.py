@@ -32,6 +32,7 @@ KIND_OF = {n: i for i, n in enumerate(KIND_NAMES)}
 
 MEM_HOST, MEM_DEVICE = 0, 1
 BATCH_ASYNC = 1
+BATCH_DEVICE_TAIL = 2
 
 
 class IALG_MemRec(C.Structure):
