@@ -423,6 +423,10 @@ static_assert(sizeof(ObjOut) == 36, "ObjOutArgsAlg layout");
 // One warp per frame, OO_WARPS_PER_CTA independent warps per CTA (they share nothing but the launch): the walk is
 // a chain of dependent shuffles and small table updates, so what hides its latency is the number of resident warps.
 constexpr int OO_WARPS_PER_CTA = 2;
+__device__ __forceinline__ void red_add_global(int32_t* p, int v)
+{
+  asm volatile("red.global.add.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 __global__ void __launch_bounds__(32 * OO_WARPS_PER_CTA)
 oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoCluster* __restrict__ clustersAll,
                   uint16_t* __restrict__ equalAll, const int maxLabels, const int tablesInSmem,
@@ -471,13 +475,21 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
   // per distinct label.  Only the cells where two DIFFERENT labels meet touch the equivalence table, and
   // those are replayed one by one, in order, exactly as the reference does (:92-102).
   const unsigned FULL = 0xFFFFFFFFu;
+  // the metapixels do not depend on the walk: the next group's word is fetched while this one is processed
+  unsigned bmNext = lane < bw ? (unsigned)bm[lane] : 0u;
   for (int row = 0; row < bh; ++row)
   {
     for (int base = 0; base < bw; base += 32)
     {
       const int col = base + lane;
       const bool inside = col < bw;
-      const bool on = inside && __popc((unsigned)bm[row * bw + col]) > 2;   // pop(...) > METAPIX_SIZE/2 (:192)
+      const unsigned bmCur = bmNext;
+      {
+        int nb = base + 32, nr = row;
+        if (nb >= bw) { nb = 0; ++nr; }
+        bmNext = (nr < bh && nb + lane < bw) ? (unsigned)bm[nr * bw + nb + lane] : 0u;
+      }
+      const bool on = inside && __popc(bmCur) > 2;                          // pop(...) > METAPIX_SIZE/2 (:192)
       // up-left, up, up-right labels (:69-83)
       uint32_t p0 = 0, p1 = 0, p2 = 0;
       if (on && row != 0)
@@ -514,6 +526,7 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
         }
       }
       ncl = min(ncl + __popc(openMask), maxLabels);
+      __syncwarp();                                                          // the zeroed records before anybody adds to them
       if (lane == 0 && on && carry != 0u)                                    // the run continues from the previous group
         x = (x == 0u || carry < x) ? carry : x;
       // segmented inclusive scan of "min over non-zero" along the runs
@@ -548,8 +561,16 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
         const int sumc = __reduce_add_sync(FULL, mine ? col : 0);
         if (lane == leader)
         {
+          // reductions without a return value: nothing in the walk waits for the table (read back only at the end)
           const int cnt = __popc(mm);
-          cl[lab].x += sumc; cl[lab].y += row * cnt; cl[lab].size += cnt;
+          if (tablesInSmem)
+          {
+            cl[lab].x += sumc; cl[lab].y += row * cnt; cl[lab].size += cnt;
+          }
+          else
+          {
+            red_add_global(&cl[lab].x, sumc); red_add_global(&cl[lab].y, row * cnt); red_add_global(&cl[lab].size, cnt);
+          }
         }
         needAdd = needAdd && !mine;
         addMask &= ~mm;
