@@ -267,6 +267,10 @@ void trikb200_setOverlapLaunch(XDAS_Int32 on);
 /* tuning knob: webcam object sensor batches whose frames share one threshold set can run through a chroma-indexed
  * detection table (results identical): 0 = automatic (default), 1 = whenever possible, -1 = never */
 void trikb200_setLutMode(XDAS_Int32 mode);
+/* tuning knob: synchronous host-memory calls of up to this many frame bytes (default 1 MiB; process() is one frame)
+ * are staged through the handle's pinned buffers by the CPU (DMA between pinned and device memory, result records
+ * written in place by the kernels); 0 = hand the caller's pointers to cudaMemcpyAsync as they are */
+void trikb200_setZeroCopyBytes(XDAS_Int32 bytes);
 /* tuning knob: frames per CTA of the wide ov7670 line kernel on small frames: 0 = heuristic (default), 1 = one, n = n */
 void trikb200_setFramesPerCta(XDAS_Int32 n);
 /* last CUDA / argument error message of this thread ("" if none) */

@@ -18,6 +18,7 @@ ARGS = {"wo": (300, 40, 20, 100, 30, 100, 0), "wl": (0, 359, 0, 100, 0, 40, 0), 
 sizes = [tuple(int(v) for v in s.split("x")) for s in (sys.argv[1] if len(sys.argv) > 1 else "320x240,640x480").split(",")]
 calls = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 pinned = len(sys.argv) > 3 and sys.argv[3] == "pinned"
+sensors.lib().trikb200_setZeroCopyBytes(int(os.environ.get("ZEROCOPY", str(1 << 20))))
 if pinned:
     import torch  # noqa: E402
 for w, h in sizes:
@@ -52,7 +53,7 @@ for w, h in sizes:
             codec.process_raw(in_bufs, out_bufs, ia, oa)
             ts.append(time.perf_counter() - t0)
         ts = np.array(ts) * 1e6
-        print(json.dumps({"sensor": kind, "size": "%dx%d" % (w, h), "calls": calls, "buffers": "pinned" if pinned else "pageable", "us_median": float(np.median(ts)),
+        print(json.dumps({"sensor": kind, "size": "%dx%d" % (w, h), "calls": calls, "zero_copy_bytes": int(os.environ.get("ZEROCOPY", str(1 << 20))), "buffers": "pinned" if pinned else "pageable", "us_median": float(np.median(ts)),
                           "us_p10": float(np.percentile(ts, 10)), "us_p90": float(np.percentile(ts, 90)),
                           "calls_per_sec": 1e6 / float(np.median(ts)),
                           "preview_bytes": int(preview.nbytes), "frame_bytes": int(frame.nbytes)}), flush=True)

@@ -50,6 +50,7 @@ def lib():
         l.trikb200_setBlockThreads.argtypes = [C.c_int32]
         l.trikb200_setOverlapLaunch.argtypes = [C.c_int32]
         l.trikb200_setLutMode.argtypes = [C.c_int32]
+        l.trikb200_setZeroCopyBytes.argtypes = [C.c_int32]
         l.trikb200_setFramesPerCta.argtypes = [C.c_int32]
         l.trikb200_lastError.restype = C.c_char_p
         l.trikb200_probePixels.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]
