@@ -267,6 +267,12 @@ void trikb200_setOverlapLaunch(XDAS_Int32 on);
 /* tuning knob: webcam object sensor batches whose frames share one threshold set can run through a chroma-indexed
  * detection table (results identical): 0 = automatic (default), 1 = whenever possible, -1 = never */
 void trikb200_setLutMode(XDAS_Int32 mode);
+/* tuning knob: the mxn sensor's per-pixel colour bin (H>>3, S>>6, V>>6) is one fixed function of (Y,U,V); batches can
+ * gather it from a 2^24-entry table built once per device (results identical):
+ * 0 = automatic (default: batches of 32 frames or more), 1 = always, -1 = never (arithmetic kernel) */
+void trikb200_setMxnTableMode(XDAS_Int32 mode);
+/* tuning knob: target CTA size of the mxn table kernel, 0 = default */
+void trikb200_setMxnTableThreads(XDAS_Int32 threads);
 /* tuning knob: synchronous host-memory calls of up to this many frame bytes (default 1 MiB; process() is one frame)
  * are staged through the handle's pinned buffers by the CPU (DMA between pinned and device memory, result records
  * written in place by the kernels); 0 = hand the caller's pointers to cudaMemcpyAsync as they are */
@@ -279,7 +285,8 @@ const char* trikb200_lastError(void);
 /* diagnostics for the parity tests: run the DEVICE pixel functions over a range of inputs.
  * which = 0: index = Y | U<<8 | V<<16 -> 0x00RRGGBB (bit 31 set if the YUYV and YUV422P lane
  * paths disagree); which = 1: index = 0x00RRGGBB -> 0x00VVSSHH (scalar form); which = 2: index = Y | U<<8 | V<<16
- * -> 0x00VVSSHH through the packed two-pixel path the sensors use (bit 31: lane paths disagree).
+ * -> 0x00VVSSHH through the packed two-pixel path the sensors use (bit 31: lane paths disagree);
+ * which = 3: index = Y | U<<8 | V<<16 -> the mxn sensor's colour bin (H>>3)<<4 | (S>>6)<<2 | V>>6 as its table holds it.
  * hostOut holds count words. */
 XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count, uint32_t* hostOut);
 /* diagnostics for the parity tests: build the chroma-indexed detection table of a webcam object sensor threshold

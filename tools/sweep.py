@@ -31,6 +31,8 @@ def main():
     import torch
     from trik_media_sensors_dsp_b200 import open_sensor, synth, xdm, sensors, launch_count
     sensors.lib().trikb200_setLutMode(int(os.environ.get("LUT", "0")))      # -1: arithmetic WO kernel only
+    sensors.lib().trikb200_setMxnTableMode(int(os.environ.get("OMTAB", "0")))   # -1: arithmetic mxn kernel only
+    sensors.lib().trikb200_setMxnTableThreads(int(os.environ.get("OMTHREADS", "0")))
     peak = 6541.1
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <ctime>
 #include <climits>
+#include <mutex>
 #include <new>
 #include <algorithm>
 #include <string>
@@ -28,6 +29,13 @@ thread_local int t_device = -1;
 int g_slabsPerFrame = 0;
 int g_zeroCopyBytes = 1 << 20;     // synchronous host batches up to this many frame bytes go through the handle's pinned staging
 int g_lutMode = 0;                 // 0 auto, 1 whenever the arguments are shared by the batch, -1 never
+int g_mxnTableMode = 0;            // mxn sensor through the colour-bin table: 0 auto (batches of >= 32 frames), 1 always, -1 never
+
+// The colour-bin table of the mxn sensor (trik_kernels_omtab.cu) depends on nothing but the device: built once per
+// device and process, on first use, and kept until the process ends.
+constexpr int MAX_DEVICES = 64;
+std::mutex g_omTableMutex;
+uint16_t* g_omTable[MAX_DEVICES] = {};
 
 void set_error(const char* what, cudaError_t e = cudaSuccess)
 {
@@ -453,6 +461,28 @@ bool ensure_lut(Instance* in, const FrameParams& fp, bool have, cudaStream_t s)
   return true;
 }
 
+// the mxn colour-bin table of a device; built (and waited for, once) on first use so that every stream may read it
+const uint16_t* ensure_om_table(int device, cudaStream_t s)
+{
+  if (device < 0 || device >= MAX_DEVICES)
+    return nullptr;
+  std::lock_guard<std::mutex> lock(g_omTableMutex);
+  if (g_omTable[device])
+    return g_omTable[device];
+  uint16_t* t = nullptr;
+  cudaError_t e = cudaMalloc(&t, OM_TABLE_BYTES);
+  if (e == cudaSuccess) e = launch_om_bin_table(t, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess)
+  {
+    set_error("mxn colour-bin table", e);
+    cudaFree(t);
+    return nullptr;
+  }
+  g_omTable[device] = t;
+  return t;
+}
+
 bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
 {
   if (!in->valid || in->geo.width <= 0 || in->geo.height <= 0)
@@ -638,7 +668,16 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
     case KIND_OM:
       if (b.outOnDevice)
         CUDA_TRY(cudaMemsetAsync(dOut, 0, recBytes * b.n, s));
-      CUDA_TRY(launch_om(g, b.n, dFrames, in->dParams, pstride, in->dMxnTable, reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s));
+      if ((g_mxnTableMode > 0 || (g_mxnTableMode == 0 && b.n >= 32)))
+      {
+        // the colour bin is one fixed function of (Y,U,V): gather it from the device's 2^24-entry table (identical results)
+        const uint16_t* binTable = ensure_om_table(in->device, s);
+        if (!binTable) return false;
+        CUDA_TRY(launch_om_table(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,
+                                 reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s));
+      }
+      else
+        CUDA_TRY(launch_om(g, b.n, dFrames, in->dParams, pstride, in->dMxnTable, reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s));
       break;
     case KIND_OO:
     {
@@ -1454,6 +1493,8 @@ void trikb200_setLoadStages(XDAS_Int32 stages) { set_sum_stages(stages); }
 void trikb200_setBlockThreads(XDAS_Int32 threads) { set_target_threads(threads); }
 void trikb200_setOverlapLaunch(XDAS_Int32 on) { set_overlap_launch(on); }
 void trikb200_setLutMode(XDAS_Int32 mode) { g_lutMode = mode; }
+void trikb200_setMxnTableMode(XDAS_Int32 mode) { g_mxnTableMode = mode; }
+void trikb200_setMxnTableThreads(XDAS_Int32 threads) { set_om_table_threads(threads); }
 void trikb200_setZeroCopyBytes(XDAS_Int32 bytes) { g_zeroCopyBytes = bytes; }
 void trikb200_setFramesPerCta(XDAS_Int32 n) { set_frames_per_cta(n); }
 const char* trikb200_lastError(void) { return t_lastError.c_str(); }
@@ -1464,8 +1505,18 @@ XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count
   uint32_t* d = nullptr;
   if (cudaMalloc(&d, (size_t)count * 4) != cudaSuccess)
     return IVIDTRANSCODE_EFAIL;
-  cudaError_t e = which == 0 ? launch_probe_yuv2rgb(first, count, d, 0)
-                : (which == 1 ? launch_probe_rgb2hsv(first, count, d, 0) : launch_probe_yuv2hsv(first, count, d, 0));
+  cudaError_t e;
+  if (which == 3)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint16_t* binTable = ensure_om_table(dev, 0);
+    if (!binTable) { cudaFree(d); return IVIDTRANSCODE_EFAIL; }
+    e = launch_om_table_probe(binTable, first, count, d, 0);
+  }
+  else
+    e = which == 0 ? launch_probe_yuv2rgb(first, count, d, 0)
+      : (which == 1 ? launch_probe_rgb2hsv(first, count, d, 0) : launch_probe_yuv2hsv(first, count, d, 0));
   if (e == cudaSuccess)
     e = cudaMemcpy(hostOut, d, (size_t)count * 4, cudaMemcpyDeviceToHost);
   cudaFree(d);

@@ -66,7 +66,8 @@ extern std::atomic<long long> g_launches_preview;
 extern std::atomic<long long> g_launches_line;
 extern std::atomic<long long> g_launches_lut;
 extern std::atomic<long long> g_launches_anneal;
-long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line + g_launches_lut + g_launches_anneal; }
+extern std::atomic<long long> g_launches_omtab;
+long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line + g_launches_lut + g_launches_anneal + g_launches_omtab; }
 
 // ---------------------------------------------------------------------------------------------
 // per-pair work

@@ -121,6 +121,14 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
 cudaError_t launch_line_bulk(bool planar, const Geometry& g, long long grid, int threads, const uint8_t* frames,
                              const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,
                              int slabs, int rowsPerSlab, int cpr, int rpi, int stages, bool overlap, cudaStream_t stream);
+// OM through the full colour-bin table (trik_kernels_omtab.cu): 2^24 uint16 entries [U][V][Y] = bin * 4
+constexpr size_t OM_TABLE_BYTES = ((size_t)1 << 24) * sizeof(uint16_t);
+cudaError_t launch_om_bin_table(uint16_t* table, cudaStream_t stream);
+cudaError_t launch_om_table_probe(const uint16_t* table, uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
+cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
+                            int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
+                            int maxGridRows, int maxGridCols, cudaStream_t stream);
+void set_om_table_threads(int threads);
 long long launch_count();
 
 } // namespace trikb200

@@ -430,7 +430,8 @@ __device__ __forceinline__ void red_add_global(int32_t* p, int v)
 __global__ void __launch_bounds__(32 * OO_WARPS_PER_CTA)
 oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoCluster* __restrict__ clustersAll,
                   uint16_t* __restrict__ equalAll, const int maxLabels, const int tablesInSmem,
-                  ObjOut* __restrict__ out, int* __restrict__ labelCounts, const int numFrames, const int smemPerWarp)
+                  ObjOut* __restrict__ out, int* __restrict__ labelCounts, const int numFrames, const int smemPerWarp,
+                  const int tailCap, const int tailOfs)
 {
   extern __shared__ __align__(16) uint8_t s_all[];
   const int frame = blockIdx.x * OO_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -601,6 +602,23 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
     }
     uint16_t* tmp = prev; prev = cur; cur = tmp;
   }
+  // The tail (merge in label order, std::sort, eight targets) is one lane's sequential work on the label tables.  In
+  // global memory every step of it is an L2 round trip; frames with few labels (the usual case) first bring their
+  // tables into this warp's corner of shared memory.
+  __syncwarp();
+  if (!tablesInSmem && ncl <= tailCap)
+  {
+    OoCluster* sc = reinterpret_cast<OoCluster*>(s_raw + tailOfs);
+    uint16_t* se = reinterpret_cast<uint16_t*>(sc + tailCap);
+    for (int i = lane; i < ncl; i += 32)
+    {
+      sc[i] = cl[i];
+      se[i] = eq[i];
+    }
+    __syncwarp();
+    cl = sc;
+    eq = se;
+  }
   if (lane != 0)
     return;
 
@@ -687,14 +705,19 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
   // that still leaves ~10 CTAs per SM (env override for A/B measurements)
   static const long smemLimit = getenv("TRIKB200_OO_SMEM_LIMIT") ? atol(getenv("TRIKB200_OO_SMEM_LIMIT")) : 4 * 1024;
   const int tablesInSmem = ((long)(tableBytes + rowBytes) <= smemLimit) ? 1 : 0;
-  const size_t smemPerWarp = ((rowBytes + (tablesInSmem ? tableBytes : 0)) + 15) & ~(size_t)15;
+  // tables in global memory: room for the tail's copy of up to tailCap labels (12 + 2 bytes each)
+  static const int tailCapEnv = getenv("TRIKB200_OO_TAIL_CAP") ? atoi(getenv("TRIKB200_OO_TAIL_CAP")) : 96;
+  const int tailCap = tablesInSmem ? 0 : (tailCapEnv < maxLabels ? tailCapEnv : maxLabels);
+  const size_t tailOfs = (rowBytes + 15) & ~(size_t)15;
+  const size_t smemPerWarp = tablesInSmem ? ((rowBytes + tableBytes + 15) & ~(size_t)15)
+                                          : ((tailOfs + (size_t)tailCap * (sizeof(OoCluster) + sizeof(uint16_t)) + 15) & ~(size_t)15);
   const size_t smem = smemPerWarp * OO_WARPS_PER_CTA;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(oo_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned ctas = (unsigned)((numFrames + OO_WARPS_PER_CTA - 1) / OO_WARPS_PER_CTA);
   oo_cluster_kernel<<<ctas, 32 * OO_WARPS_PER_CTA, smem, stream>>>(g, bitmaps, reinterpret_cast<OoCluster*>(clusters), equal,
                                                                    maxLabels, tablesInSmem, reinterpret_cast<ObjOut*>(out), labelCounts,
-                                                                   numFrames, (int)smemPerWarp);
+                                                                   numFrames, (int)smemPerWarp, tailCap, (int)tailOfs);
   ++g_launches_grid;
   return cudaGetLastError();
 }

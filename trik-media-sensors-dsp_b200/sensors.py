@@ -50,6 +50,8 @@ def lib():
         l.trikb200_setBlockThreads.argtypes = [C.c_int32]
         l.trikb200_setOverlapLaunch.argtypes = [C.c_int32]
         l.trikb200_setLutMode.argtypes = [C.c_int32]
+        l.trikb200_setMxnTableMode.argtypes = [C.c_int32]
+        l.trikb200_setMxnTableThreads.argtypes = [C.c_int32]
         l.trikb200_setZeroCopyBytes.argtypes = [C.c_int32]
         l.trikb200_setFramesPerCta.argtypes = [C.c_int32]
         l.trikb200_lastError.restype = C.c_char_p
