@@ -706,7 +706,7 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
   static const long smemLimit = getenv("TRIKB200_OO_SMEM_LIMIT") ? atol(getenv("TRIKB200_OO_SMEM_LIMIT")) : 4 * 1024;
   const int tablesInSmem = ((long)(tableBytes + rowBytes) <= smemLimit) ? 1 : 0;
   // tables in global memory: room for the tail's copy of up to tailCap labels (12 + 2 bytes each)
-  static const int tailCapEnv = getenv("TRIKB200_OO_TAIL_CAP") ? atoi(getenv("TRIKB200_OO_TAIL_CAP")) : 96;
+  static const int tailCapEnv = getenv("TRIKB200_OO_TAIL_CAP") ? atoi(getenv("TRIKB200_OO_TAIL_CAP")) : 256;
   const int tailCap = tablesInSmem ? 0 : (tailCapEnv < maxLabels ? tailCapEnv : maxLabels);
   const size_t tailOfs = (rowBytes + 15) & ~(size_t)15;
   const size_t smemPerWarp = tablesInSmem ? ((rowBytes + tableBytes + 15) & ~(size_t)15)
