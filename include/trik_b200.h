@@ -237,6 +237,35 @@ typedef struct TRIKB200_MixedEntry {
 } TRIKB200_MixedEntry;
 XDAS_Int32 trikb200_processMixed(const TRIKB200_MixedEntry* entries, XDAS_Int32 numEntries);
 
+/* Ingest front end: packed RGB565 camera frames -> the YUV422P layout the ov7670 sensors read
+ * (luma plane, then at dstLineLength * height the plane of interleaved chroma bytes V U V U ...), so that an RGB565 stream
+ * can feed trikb200_processBatch of an ov7670 handle (frames = dst, frameStride = dstStride, framesMem = dstMem).
+ * The reference itself has no RGB565 INPUT (its ov7670 sensors accept YUV422P only, src/vidtranscode_cv.cpp:76-84;
+ * RGB565X is the format of the preview they write), so the arithmetic is defined here and pinned by nothing in the
+ * reference: integer BT.601 studio swing, the inverse of the reference's own YUV -> RGB matrix --
+ *   R8 = r5<<3 | r5>>2, G8 = g6<<2 | g6>>4, B8 = b5<<3 | b5>>2,
+ *   Y = ((66R + 129G + 25B + 128) >> 8) + 16; chroma of a pixel pair from its summed channels Rs = R0 + R1, Gs, Bs:
+ *   Cb = ((-38Rs - 74Gs + 112Bs + 256) >> 9) + 128, Cr = ((112Rs - 94Gs - 18Bs + 256) >> 9) + 128 (shifts floor). */
+#define TRIKB200_PIXEL_RGB565   0   /* 16-bit little-endian words: R in bits 15..11, G 10..5, B 4..0 */
+#define TRIKB200_PIXEL_RGB565X  1   /* B in bits 15..11, G 10..5, R 4..0: the words the sensors' preview images hold
+                                       (writeOutputPixel, webcam/object_sensor/include/internal/cv_ball_detector_seqpass.hpp:66-70) */
+typedef struct TRIKB200_Ingest {
+    XDAS_Int32  size;            /* sizeof(TRIKB200_Ingest) */
+    XDAS_Int32  numFrames;
+    XDAS_Int32  width, height;   /* pixels, width % 8 == 0 */
+    XDAS_Int32  pixelFormat;     /* TRIKB200_PIXEL_* */
+    XDAS_Int32  srcMem, dstMem;  /* TRIKB200_MEM_* */
+    XDAS_Int32  srcLineLength;   /* bytes per source row, >= 2 * width, multiple of 16 */
+    XDAS_Int32  dstLineLength;   /* bytes per row of each destination plane, >= width, multiple of 8 */
+    const void* src;             /* frame i at src + i * srcStride (16-byte aligned) */
+    int64_t     srcStride;
+    void*       dst;             /* frame i at dst + i * dstStride (8-byte aligned), 2 * dstLineLength * height bytes each */
+    int64_t     dstStride;
+    void*       stream;          /* cudaStream_t, NULL = the default stream.  With device memory on both sides the
+                                    conversion is only enqueued; with host memory the call returns when dst is complete */
+} TRIKB200_Ingest;
+XDAS_Int32 trikb200_ingestRgb565(const TRIKB200_Ingest* ingest);
+
 /* wait for everything enqueued on the handle (TRIKB200_BATCH_ASYNC) */
 XDAS_Int32 trikb200_synchronize(IVIDTRANSCODE_Handle handle);
 

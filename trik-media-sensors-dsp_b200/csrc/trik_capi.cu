@@ -1528,6 +1528,59 @@ XDAS_Int32 trikb200_probePixels(XDAS_Int32 which, uint32_t first, uint32_t count
   return IVIDTRANSCODE_EOK;
 }
 
+XDAS_Int32 trikb200_ingestRgb565(const TRIKB200_Ingest* d)
+{
+  if (!d || d->size != (XDAS_Int32)sizeof(TRIKB200_Ingest) || d->numFrames < 0 || !d->src || !d->dst
+      || (d->pixelFormat != TRIKB200_PIXEL_RGB565 && d->pixelFormat != TRIKB200_PIXEL_RGB565X))
+  {
+    set_error("ingestRgb565: bad descriptor");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if (d->numFrames == 0)
+    return IVIDTRANSCODE_EOK;
+  cudaStream_t s = static_cast<cudaStream_t>(d->stream);
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t srcFrame = (size_t)d->srcLineLength * d->height, dstFrame = (size_t)2 * d->dstLineLength * d->height;
+  const bool srcHost = d->srcMem != TRIKB200_MEM_DEVICE, dstHost = d->dstMem != TRIKB200_MEM_DEVICE;
+  uint8_t *dSrc = nullptr, *dDst = nullptr;
+  const uint8_t* src = static_cast<const uint8_t*>(d->src);
+  uint8_t* dst = static_cast<uint8_t*>(d->dst);
+  long long srcStride = d->srcStride, dstStride = d->dstStride;
+  if (e == cudaSuccess && srcHost)
+  {
+    e = cudaMalloc(&dSrc, srcFrame * d->numFrames);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(dSrc, srcFrame, src, (size_t)d->srcStride, srcFrame, (size_t)d->numFrames, cudaMemcpyHostToDevice, s);
+    src = dSrc; srcStride = (long long)srcFrame;
+  }
+  if (e == cudaSuccess && dstHost)
+  {
+    e = cudaMalloc(&dDst, dstFrame * d->numFrames);
+    dst = dDst; dstStride = (long long)dstFrame;
+  }
+  if (e == cudaSuccess)
+    e = launch_ingest_rgb565(src, srcStride, d->srcLineLength, dst, dstStride, d->dstLineLength, d->width, d->height,
+                             d->numFrames, d->pixelFormat == TRIKB200_PIXEL_RGB565X ? 1 : 0, sms, s);
+  if (e == cudaSuccess && dstHost)
+    e = cudaMemcpy2DAsync(d->dst, (size_t)d->dstStride, dDst, dstFrame, dstFrame, (size_t)d->numFrames, cudaMemcpyDeviceToHost, s);
+  if (srcHost || dstHost)
+  {
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
+    cudaFree(dSrc);
+    cudaFree(dDst);
+  }
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    set_error("ingestRgb565", e);
+    return IVIDTRANSCODE_EFAIL;
+  }
+  return IVIDTRANSCODE_EOK;
+}
+
 XDAS_Int32 trikb200_probeLut(const TRIKB200_RangeInArgsAlg* inArgsAlg, uint64_t stats[5])
 {
   Geometry g{};

@@ -129,6 +129,9 @@ cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* fra
                             int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
                             int maxGridRows, int maxGridCols, cudaStream_t stream);
 void set_om_table_threads(int threads);
+// RGB565 -> YUV422P ingest front end (trik_kernels_ingest.cu)
+cudaError_t launch_ingest_rgb565(const uint8_t* src, long long srcStride, int srcLine, uint8_t* dst, long long dstStride,
+                                 int dstLine, int width, int height, int numFrames, int bgr, int smCount, cudaStream_t stream);
 long long launch_count();
 
 } // namespace trikb200

@@ -57,11 +57,32 @@ def lib():
         l.trikb200_lastError.restype = C.c_char_p
         l.trikb200_probePixels.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, C.c_void_p]
         l.trikb200_probeLut.argtypes = [C.c_void_p, C.c_void_p]
+        l.trikb200_ingestRgb565.argtypes = [C.POINTER(xdm.Ingest)]
+        l.trikb200_ingestRgb565.restype = C.c_int32
         for f in ("trikb200_sizeofInArgsAlg", "trikb200_sizeofOutArgsAlg", "trikb200_sizeofInArgs",
                   "trikb200_sizeofOutArgs"):
             getattr(l, f).argtypes = [C.c_int32]
         _lib = l
     return _lib
+
+
+def ingest_rgb565(src, width, height, pixel_format=xdm.PIXEL_RGB565, src_line_length=None, out=None):
+    """Host-memory form of trikb200_ingestRgb565: src (n, src_line_length * height) uint8 holding packed RGB565 (or
+    RGB565X) rows -> (n, 2 * width * height) uint8 YUV422P frames as the ov7670 sensors read them."""
+    assert src.dtype == np.uint8 and src.ndim == 2 and src.flags["C_CONTIGUOUS"]
+    line = 2 * width if src_line_length is None else src_line_length
+    n = src.shape[0]
+    if out is None:
+        out = np.empty((n, 2 * width * height), np.uint8)
+    d = xdm.Ingest()
+    d.size = C.sizeof(d)
+    d.numFrames, d.width, d.height, d.pixelFormat = n, width, height, pixel_format
+    d.srcMem, d.dstMem = xdm.MEM_HOST, xdm.MEM_HOST
+    d.srcLineLength, d.dstLineLength = line, width
+    d.src, d.srcStride = src.ctypes.data, src.strides[0]
+    d.dst, d.dstStride = out.ctypes.data, out.strides[0]
+    ret = lib().trikb200_ingestRgb565(C.byref(d))
+    return ret, out
 
 
 def last_error():

@@ -198,6 +198,18 @@ class Batch(C.Structure):
                 ("previews", C.c_void_p), ("previewStride", C.c_int64), ("previewsMem", C.c_int32)]
 
 
+class Ingest(C.Structure):
+    """TRIKB200_Ingest (include/trik_b200.h): RGB565 -> YUV422P front end."""
+    _fields_ = [("size", C.c_int32), ("numFrames", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("pixelFormat", C.c_int32), ("srcMem", C.c_int32), ("dstMem", C.c_int32),
+                ("srcLineLength", C.c_int32), ("dstLineLength", C.c_int32),
+                ("src", C.c_void_p), ("srcStride", C.c_int64), ("dst", C.c_void_p), ("dstStride", C.c_int64),
+                ("stream", C.c_void_p)]
+
+
+PIXEL_RGB565, PIXEL_RGB565X = 0, 1
+
+
 class MixedEntry(C.Structure):
     _fields_ = [("handle", C.c_void_p), ("frame", C.c_void_p), ("inArgsAlg", C.c_void_p), ("outArgsAlg", C.c_void_p),
                 ("seed", C.c_int64)]
