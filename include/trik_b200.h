@@ -297,8 +297,8 @@ void trikb200_setOverlapLaunch(XDAS_Int32 on);
  * detection table (results identical): 0 = automatic (default), 1 = whenever possible, -1 = never */
 void trikb200_setLutMode(XDAS_Int32 mode);
 /* tuning knob: the mxn sensor's per-pixel colour bin (H>>3, S>>6, V>>6) is one fixed function of (Y,U,V); batches can
- * gather it from a 2^24-entry table built once per device (results identical):
- * 0 = automatic (default: batches of 32 frames or more), 1 = always, -1 = never (arithmetic kernel) */
+ * gather it from a 2^24-entry table built once per device and process, at the first mxn call (32 MB; results identical,
+ * see DESIGN.md 3.4): 0 or 1 = yes (default; measured faster from a single frame up), -1 = never (arithmetic kernel) */
 void trikb200_setMxnTableMode(XDAS_Int32 mode);
 /* tuning knob: target CTA size of the mxn table kernel, 0 = default */
 void trikb200_setMxnTableThreads(XDAS_Int32 threads);

@@ -94,8 +94,8 @@ def main():
         seeds = [(7 + i * 2654435761) % 2147483647 for i in range(sub)]
         ia = xdm.ObjInArgsAlg(1, 0, 40, 60, 40, 60, 40, 1) if kind == "oo" else xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 100, 1)
         codec = open_sensor(kind, w, h)
-        codec.process_batch(frames[:8], ia, seeds=seeds[:8])
-        codec.set_params(w, h)
+        codec.process_batch(frames, ia, seeds=seeds)                     # warm-up at full size (allocations, tables, threads)
+        codec.set_params(w, h)                                           # fresh carried state, as the oracle below starts from
         t0 = time.perf_counter()
         ret, outs = codec.process_batch(frames, ia, seeds=seeds)
         dt = time.perf_counter() - t0

@@ -19,10 +19,14 @@ sizes = [tuple(int(v) for v in s.split("x")) for s in (sys.argv[1] if len(sys.ar
 calls = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 pinned = len(sys.argv) > 3 and sys.argv[3] == "pinned"
 sensors.lib().trikb200_setZeroCopyBytes(int(os.environ.get("ZEROCOPY", str(1 << 20))))
+sensors.lib().trikb200_setMxnTableMode(int(os.environ.get("OMTAB", "0")))
+only = os.environ.get("KINDS", "").split(",") if os.environ.get("KINDS") else None
 if pinned:
     import torch  # noqa: E402
 for w, h in sizes:
     for kind in xdm.KIND_NAMES:
+        if only and kind not in only:
+            continue
         layout = sensors.layout_of(xdm.KIND_OF[kind])
         frame = synth.make_frame("blobs" if kind == "oo" else ("grid" if kind == "om" else "scene"), 1, w, h, layout)
         codec = open_sensor(kind, w, h)

@@ -29,7 +29,7 @@ thread_local int t_device = -1;
 int g_slabsPerFrame = 0;
 int g_zeroCopyBytes = 1 << 20;     // synchronous host batches up to this many frame bytes go through the handle's pinned staging
 int g_lutMode = 0;                 // 0 auto, 1 whenever the arguments are shared by the batch, -1 never
-int g_mxnTableMode = 0;            // mxn sensor through the colour-bin table: 0 auto (batches of >= 32 frames), 1 always, -1 never
+int g_mxnTableMode = 0;            // mxn sensor through the colour-bin table: 0 / 1 yes (default), -1 never (arithmetic kernel)
 
 // The colour-bin table of the mxn sensor (trik_kernels_omtab.cu) depends on nothing but the device: built once per
 // device and process, on first use, and kept until the process ends.
@@ -668,7 +668,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
     case KIND_OM:
       if (b.outOnDevice)
         CUDA_TRY(cudaMemsetAsync(dOut, 0, recBytes * b.n, s));
-      if ((g_mxnTableMode > 0 || (g_mxnTableMode == 0 && b.n >= 32)))
+      if (g_mxnTableMode >= 0)
       {
         // the colour bin is one fixed function of (Y,U,V): gather it from the device's 2^24-entry table (identical results)
         const uint16_t* binTable = ensure_om_table(in->device, s);
