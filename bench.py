@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sustained", action="store_true", help="skip the 1.5 s steady-state phase")
     ap.add_argument("--no-repeats", action="store_true", help="time the K steps once only")
+    ap.add_argument("--no-others", action="store_true", help="skip the short resident measurement of the other four sensors")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -380,6 +381,39 @@ def main():
         }
         line["config"]["host_affinity"] = ("rank bound to its GPU's NUMA node: %d of %d CPUs" % (len(bound[1]), len(bound[0]))
                                            if bound else "unbound (NVML affinity query unavailable)")
+        if not args.no_others and world == 1:
+            # beside the headline: the other four sensors on the same batch shape, frames resident, 10 steps each
+            # (explanatory only -- `value` above is the BASELINE metric)
+            others = {}
+            from trik_media_sensors_dsp_b200 import sensors as _sensors
+            for kind in ("ol", "wo", "om", "oo"):
+                layout = _sensors.layout_of(xdm.KIND_OF[kind])
+                fam = "grid" if kind == "om" else "scene"
+                hu = synth.make_batch(fam, range(uniq), W, H, layout)
+                hv[:] = 0
+                for i in range(0, n, uniq):
+                    hv[i:i + uniq] = hu[:min(uniq, n - i)]
+                d_frames.copy_(host)
+                k = xdm.KIND_OF[kind]
+                orec = C.sizeof(xdm.OUT_ARGS_ALG[k])
+                o_out = torch.zeros((n, orec), dtype=torch.uint8, device=dev)
+                oc = open_sensor(kind, W, H)
+                oia = (xdm.ObjInArgsAlg(1, 0, 20, 80, 20, 50, 30, 0) if kind == "oo"
+                       else (xdm.MxnInArgsAlg(3, 3) if kind == "om" else xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 40, 0)))
+
+                def other_step():
+                    r, _ = oc.process_batch(d_frames.data_ptr(), oia, frames_device=True, frame_stride=fbytes, num_frames=n,
+                                            out_device_ptr=o_out.data_ptr(), stream=sptr, flags=xdm.BATCH_ASYNC)
+                    assert r == 0
+
+                for _ in range(3):
+                    other_step()
+                oms = timed(other_step, 10) / 10
+                others[kind] = {"frames_per_sec": n / (oms / 1000.0), "ms_per_step": oms,
+                                "hbm_frac": n * W * H * 2 / (oms / 1000.0) / 1e9 / peak, "frames": fam}
+                oc.close()
+                del o_out
+            line["other_sensors"] = others
         if not args.no_cpu and world == 1:
             if bound:
                 os.sched_setaffinity(0, bound[0])          # the CPU baseline uses every core of the box again
