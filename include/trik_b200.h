@@ -240,6 +240,7 @@ XDAS_Int32 trikb200_processMixed(const TRIKB200_MixedEntry* entries, XDAS_Int32 
 /* Ingest front end: packed RGB565 camera frames -> the YUV422P layout the ov7670 sensors read
  * (luma plane, then at dstLineLength * height the plane of interleaved chroma bytes V U V U ...), so that an RGB565 stream
  * can feed trikb200_processBatch of an ov7670 handle (frames = dst, frameStride = dstStride, framesMem = dstMem).
+ * Runs on the calling thread's current CUDA device (trikb200_setDevice); needs no handle.
  * The reference itself has no RGB565 INPUT (its ov7670 sensors accept YUV422P only, src/vidtranscode_cv.cpp:76-84;
  * RGB565X is the format of the preview they write), so the arithmetic is defined here and pinned by nothing in the
  * reference: integer BT.601 studio swing, the inverse of the reference's own YUV -> RGB matrix --
