@@ -423,6 +423,7 @@ static_assert(sizeof(ObjOut) == 36, "ObjOutArgsAlg layout");
 // One warp per frame, OO_WARPS_PER_CTA independent warps per CTA (they share nothing but the launch): the walk is
 // a chain of dependent shuffles and small table updates, so what hides its latency is the number of resident warps.
 constexpr int OO_WARPS_PER_CTA = 2;
+constexpr int OO_RING_ROWS = 8, OO_RING_AHEAD = 7;        // bitmap rows staged in shared memory / rows fetched ahead
 __device__ __forceinline__ void red_add_global(int32_t* p, int v)
 {
   asm volatile("red.global.add.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(32 * OO_WARPS_PER_CTA)
 oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoCluster* __restrict__ clustersAll,
                   uint16_t* __restrict__ equalAll, const int maxLabels, const int tablesInSmem,
                   ObjOut* __restrict__ out, int* __restrict__ labelCounts, const int numFrames, const int smemPerWarp,
-                  const int tailCap, const int tailOfs)
+                  const int tailCap, const int tailOfs, const int ringOfs)
 {
   extern __shared__ __align__(16) uint8_t s_all[];
   const int frame = blockIdx.x * OO_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -476,20 +477,44 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
   // per distinct label.  Only the cells where two DIFFERENT labels meet touch the equivalence table, and
   // those are replayed one by one, in order, exactly as the reference does (:92-102).
   const unsigned FULL = 0xFFFFFFFFu;
-  // the metapixels do not depend on the walk: the next group's word is fetched while this one is processed
-  unsigned bmNext = lane < bw ? (unsigned)bm[lane] : 0u;
+  // The metapixels do not depend on the walk, but the walk is a chain of short dependent steps: a bitmap word fetched
+  // one group ahead arrives after ~500 cycles while an empty group takes ~100.  So whole bitmap rows are staged
+  // OO_RING_AHEAD rows ahead into a small ring in shared memory with cp.async, one commit group per row.
+  uint16_t* const ring = reinterpret_cast<uint16_t*>(s_raw + ringOfs);
+  auto issue_row = [&](int r)
+  {
+    if (r < bh)
+      for (int c = lane; c < (bw >> 3); c += 32)
+        cp_async16(ring + (size_t)(r & (OO_RING_ROWS - 1)) * bw + c * 8, bm + (size_t)r * bw + c * 8);
+    cp_async_commit();                                                       // also when empty: the group count stays uniform
+  };
+  for (int r = 0; r < OO_RING_AHEAD; ++r)
+    issue_row(r);
   for (int row = 0; row < bh; ++row)
   {
+    issue_row(row + OO_RING_AHEAD);                                          // overwrites the slot of row - 1, fully read by now
+    cp_async_wait<OO_RING_AHEAD>();                                          // all but the newest groups: this row has landed
+    __syncwarp();
+    const uint16_t* const bmRow = ring + (size_t)(row & (OO_RING_ROWS - 1)) * bw;
+    {
+      // a row without a single detected cell (most rows of most frames): its labels are all 0, nothing else happens
+      bool anyOn = false;
+      for (int c = lane; c < bw; c += 32)
+        anyOn |= __popc((unsigned)bmRow[c]) > 2;
+      if (!__any_sync(FULL, anyOn))
+      {
+        for (int c = lane; c < bw; c += 32)
+          cur[c] = 0;
+        __syncwarp();
+        uint16_t* tmp = prev; prev = cur; cur = tmp;
+        continue;
+      }
+    }
     for (int base = 0; base < bw; base += 32)
     {
       const int col = base + lane;
       const bool inside = col < bw;
-      const unsigned bmCur = bmNext;
-      {
-        int nb = base + 32, nr = row;
-        if (nb >= bw) { nb = 0; ++nr; }
-        bmNext = (nr < bh && nb + lane < bw) ? (unsigned)bm[nr * bw + nb + lane] : 0u;
-      }
+      const unsigned bmCur = inside ? (unsigned)bmRow[col] : 0u;
       const bool on = inside && __popc(bmCur) > 2;                          // pop(...) > METAPIX_SIZE/2 (:192)
       // up-left, up, up-right labels (:69-83)
       uint32_t p0 = 0, p1 = 0, p2 = 0;
@@ -550,31 +575,27 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
       uint32_t L = __shfl_up_sync(FULL, v, 1);
       if (lane == 0) L = carry;
       if (!on) L = 0u;
-      // masses: every on cell except the openers adds (col, row, 1) to its label
-      bool needAdd = on && !opens && v != 0u;
-      unsigned addMask = __ballot_sync(FULL, needAdd);
-      while (addMask)
+      // masses: every on cell except the openers adds (col, row, 1) to its label.  The cells of one label find each
+      // other with one MATCH; the lowest lane of each group adds for all of them (sum of their columns from the bit
+      // positions of the peer mask), all labels of the group at once.
       {
-        const int leader = __ffs((int)addMask) - 1;
-        const uint32_t lab = __shfl_sync(FULL, v, leader);
-        const bool mine = needAdd && v == lab;
-        const unsigned mm = __ballot_sync(FULL, mine);
-        const int sumc = __reduce_add_sync(FULL, mine ? col : 0);
-        if (lane == leader)
+        const bool needAdd = on && !opens && v != 0u;
+        const unsigned peers = __match_any_sync(FULL, needAdd ? v : 0xFFFFFFFFu);
+        if (needAdd && lane == __ffs((int)peers) - 1)
         {
+          const int cnt = __popc(peers);
+          const int sumc = base * cnt + __popc(peers & 0xAAAAAAAAu) + 2 * __popc(peers & 0xCCCCCCCCu)
+                         + 4 * __popc(peers & 0xF0F0F0F0u) + 8 * __popc(peers & 0xFF00FF00u) + 16 * __popc(peers & 0xFFFF0000u);
           // reductions without a return value: nothing in the walk waits for the table (read back only at the end)
-          const int cnt = __popc(mm);
           if (tablesInSmem)
           {
-            cl[lab].x += sumc; cl[lab].y += row * cnt; cl[lab].size += cnt;
+            cl[v].x += sumc; cl[v].y += row * cnt; cl[v].size += cnt;
           }
           else
           {
-            red_add_global(&cl[lab].x, sumc); red_add_global(&cl[lab].y, row * cnt); red_add_global(&cl[lab].size, cnt);
+            red_add_global(&cl[v].x, sumc); red_add_global(&cl[v].y, row * cnt); red_add_global(&cl[v].size, cnt);
           }
         }
-        needAdd = needAdd && !mine;
-        addMask &= ~mm;
       }
       // equivalences: only where a different non-zero label touches the cell, replayed in raster order
       const bool meets = on && !opens && v != 0u &&
@@ -709,15 +730,17 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
   static const int tailCapEnv = getenv("TRIKB200_OO_TAIL_CAP") ? atoi(getenv("TRIKB200_OO_TAIL_CAP")) : 256;
   const int tailCap = tablesInSmem ? 0 : (tailCapEnv < maxLabels ? tailCapEnv : maxLabels);
   const size_t tailOfs = (rowBytes + 15) & ~(size_t)15;
-  const size_t smemPerWarp = tablesInSmem ? ((rowBytes + tableBytes + 15) & ~(size_t)15)
-                                          : ((tailOfs + (size_t)tailCap * (sizeof(OoCluster) + sizeof(uint16_t)) + 15) & ~(size_t)15);
+  const size_t ringBytes = (size_t)OO_RING_ROWS * (g.width / 4) * sizeof(uint16_t);
+  const size_t ringOfs = tablesInSmem ? ((rowBytes + tableBytes + 15) & ~(size_t)15)
+                                      : ((tailOfs + (size_t)tailCap * (sizeof(OoCluster) + sizeof(uint16_t)) + 15) & ~(size_t)15);
+  const size_t smemPerWarp = (ringOfs + ringBytes + 15) & ~(size_t)15;
   const size_t smem = smemPerWarp * OO_WARPS_PER_CTA;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(oo_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned ctas = (unsigned)((numFrames + OO_WARPS_PER_CTA - 1) / OO_WARPS_PER_CTA);
   oo_cluster_kernel<<<ctas, 32 * OO_WARPS_PER_CTA, smem, stream>>>(g, bitmaps, reinterpret_cast<OoCluster*>(clusters), equal,
                                                                    maxLabels, tablesInSmem, reinterpret_cast<ObjOut*>(out), labelCounts,
-                                                                   numFrames, (int)smemPerWarp, tailCap, (int)tailOfs);
+                                                                   numFrames, (int)smemPerWarp, tailCap, (int)tailOfs, (int)ringOfs);
   ++g_launches_grid;
   return cudaGetLastError();
 }
