@@ -53,7 +53,10 @@ def main():
                 n //= 2
             uniq = min(args.unique, n)
             fam = "grid" if (kind == "om" and args.family == "scene") else args.family
-            hu = synth.make_batch(fam, range(uniq), w, h, layout, m=gm, n=gn) if fam == "grid" else synth.make_batch(fam, range(uniq), w, h, layout)
+            if fam == "grid" or (fam == "camera" and kind == "om"):
+                hu = synth.make_batch(fam, range(uniq), w, h, layout, m=gm, n=gn)
+            else:
+                hu = synth.make_batch(fam, range(uniq), w, h, layout)
             host = torch.empty((n, fbytes), dtype=torch.uint8)
             hv = host.numpy()
             for i in range(0, n, uniq):

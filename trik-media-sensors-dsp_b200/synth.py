@@ -113,6 +113,29 @@ def planes_scene(seed, w, h, band=True):
     return y.astype(np.uint8), u.astype(np.uint8), v.astype(np.uint8)
 
 
+def planes_camera(seed, w, h, m=0, n=0):
+    """A scene (or, with m x n given, a painted grid) as a real sensor delivers it: independent noise of +-2 LSB on the
+    luma AND on both chroma channels of every sample."""
+    if m and n:
+        p = _randint(seed, 20, 0, 256, 3 * m * n)
+        y = np.zeros((h, w), dtype=np.int32)
+        u = np.zeros((h, w // 2), dtype=np.int32)
+        v = np.zeros((h, w // 2), dtype=np.int32)
+        hs, ws = h // m, w // n
+        for i in range(m):
+            for j in range(n):
+                k = 3 * (i * n + j)
+                y[i * hs:(i + 1) * hs, j * ws:(j + 1) * ws] = 32 + p[k] % 208
+                u[i * hs:(i + 1) * hs, (j * ws) // 2:((j + 1) * ws) // 2] = p[k + 1]
+                v[i * hs:(i + 1) * hs, (j * ws) // 2:((j + 1) * ws) // 2] = p[k + 2]
+    else:
+        y, u, v = (a.astype(np.int32) for a in planes_scene(seed, w, h))
+    y = y + (_rand_bytes(seed, w * h, 31).reshape(h, w) % 5).astype(np.int32) - 2
+    u = u + (_rand_bytes(seed, w * h // 2, 32).reshape(h, w // 2) % 5).astype(np.int32) - 2
+    v = v + (_rand_bytes(seed, w * h // 2, 33).reshape(h, w // 2) % 5).astype(np.int32) - 2
+    return (np.clip(y, 0, 255).astype(np.uint8), np.clip(u, 0, 255).astype(np.uint8), np.clip(v, 0, 255).astype(np.uint8))
+
+
 def planes_grid(seed, w, h, m, n):
     """m rows x n columns of cells (the mxn sensor's widthM x heightN, names as the reference swaps them)."""
     p = _randint(seed, 20, 0, 256, 3 * m * n)
@@ -216,7 +239,7 @@ def planes_edge(name, w, h):
 
 
 def make_frame(family, seed, w, h, layout, line_length=None, **kw):
-    """Flat uint8 frame.  family: 'noise' | 'scene' | 'grid' | one of EDGE_CASES."""
+    """Flat uint8 frame.  family: 'noise' | 'scene' | 'grid' | 'blobs' | 'camera' | one of EDGE_CASES."""
     if family == "noise":
         planes = planes_noise(seed, w, h)
     elif family == "scene":
@@ -225,6 +248,8 @@ def make_frame(family, seed, w, h, layout, line_length=None, **kw):
         planes = planes_grid(seed, w, h, kw.get("m", 3), kw.get("n", 3))
     elif family == "blobs":
         planes = planes_blobs(seed, w, h)
+    elif family == "camera":
+        planes = planes_camera(seed, w, h, kw.get("m", 0), kw.get("n", 0))
     else:
         planes = planes_edge(family, w, h)
     return pack(planes[0], planes[1], planes[2], layout, line_length)
