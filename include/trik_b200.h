@@ -301,6 +301,10 @@ void trikb200_setLutMode(XDAS_Int32 mode);
  * gather it from a 2^24-entry table built once per device and process, at the first mxn call (32 MB; results identical,
  * see DESIGN.md 3.4): 0 or 1 = yes (default; measured faster from a single frame up), -1 = never (arithmetic kernel) */
 void trikb200_setMxnTableMode(XDAS_Int32 mode);
+/* tuning knob: 1 (default) = the shared-memory detection table of the object sensors is laid out with skewed rows (260
+ * instead of 256 bytes apart): no bank conflicts when the chroma of neighbouring pixels differs by a little (camera noise),
+ * for one more instruction per pixel pair (+60..75 % on such frames, -4 % on frames with noise-free chroma); 0 = plain rows */
+void trikb200_setLutSkew(XDAS_Int32 on);
 /* tuning knob: target CTA size of the mxn table kernel, 0 = default */
 void trikb200_setMxnTableThreads(XDAS_Int32 threads);
 /* tuning knob: synchronous host-memory calls of up to this many frame bytes (default 1 MiB; process() is one frame)

@@ -102,3 +102,26 @@ def test_oo_bitmap_through_table_matches_oracle(size):
             got = [bytes(memoryview(o))[:24] for o in outs]
             assert got == want, (size, args, mode, [i for i in range(len(got)) if got[i] != want[i]][:8])
     codec.close()
+
+
+@pytest.mark.parametrize("size", [(320, 240), (96, 8), (640, 480)])
+def test_skewed_table_layout_gives_the_same_bytes(size):
+    """trikb200_setLutSkew: rows of the shared-memory table 260 (default) or 256 bytes apart -- same results."""
+    w, h = size
+    fams = [("camera", s) for s in range(4)] + [("noise", s) for s in range(3)] + [("scene", 1), ("bluewrap", 0), ("full", 0)]
+    frames = np.concatenate([np.stack([synth.make_frame(f, s, w, h, "yuyv") for f, s in fams])] * 3)
+    codec = open_sensor("wo", w, h)
+    try:
+        for args in THRESHOLDS[:6]:
+            orc = oracle.OracleSensor("wo", w, h)
+            want = [bytes(memoryview(orc.process(frames[i], oracle.RangeInArgs(*args))[1]))[:3] for i in range(len(fams))] * 3
+            lib().trikb200_setLutMode(1)
+            for skew in (1, 0):
+                lib().trikb200_setLutSkew(skew)
+                ret, outs = codec.process_batch(frames, xdm.RangeInArgsAlg(*args))
+                assert ret == 0, lib().trikb200_lastError()
+                got = [bytes(memoryview(o))[:3] for o in outs]
+                assert got == want, (size, args, skew, [i for i in range(len(got)) if got[i] != want[i]][:8])
+    finally:
+        lib().trikb200_setLutSkew(1)
+        codec.close()

@@ -107,8 +107,8 @@ void set_overlap_launch(int on);
 cudaError_t launch_anneal(int kind, int numFlagged, const int* frameIdx, const int32_t* hist, const uint32_t* seeds,
                           void* out, cudaStream_t stream);
 void set_frames_per_cta(int n);
-// chroma-indexed detection table (trik_kernels_lut.cu): 2 x 65 536 bytes + 65 536 x 8 x uint32
-constexpr size_t LUT_TABLE_BYTES = 2 * 65536;
+// chroma-indexed detection table (trik_kernels_lut.cu): 2 x 65 536 bytes (+ the skewed copy) + 65 536 x 8 x uint32
+constexpr size_t LUT_TABLE_BYTES = 2 * 65536 + 2 * 66560;    // plain image, then the skewed image (rows 260 bytes apart)
 constexpr size_t LUT_MASK_BYTES  = (size_t)65536 * 8 * sizeof(uint32_t);
 cudaError_t launch_chroma_table(uint32_t from, uint32_t to, uint32_t expected, uint8_t* table, uint32_t* masks,
                                 cudaStream_t stream);
@@ -129,6 +129,7 @@ cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* fra
                             int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
                             int maxGridRows, int maxGridCols, cudaStream_t stream);
 void set_om_table_threads(int threads);
+void set_lut_skew(int on);
 // RGB565 -> YUV422P ingest front end (trik_kernels_ingest.cu)
 cudaError_t launch_ingest_rgb565(const uint8_t* src, long long srcStride, int srcLine, uint8_t* dst, long long dstStride,
                                  int dstLine, int width, int height, int numFrames, int bgr, int smCount, cudaStream_t stream);

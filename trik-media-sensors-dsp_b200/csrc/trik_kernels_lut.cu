@@ -32,11 +32,15 @@
 namespace trikb200 {
 
 std::atomic<long long> g_launches_lut{0};
+static int g_lutSkew = 1;
+void set_lut_skew(int on) { g_lutSkew = on; }
 
 // (lo, nhi = 255 - hi) codes with lo > hi: no luma satisfies lo <= Y <= hi, so the interval test fails by itself
 constexpr uint32_t LUT_NEVER_LO = 255u, LUT_NEVER_NHI = 255u;        // hi = 0
 constexpr uint32_t LUT_RAGGED_LO = 255u, LUT_RAGGED_NHI = 254u;      // hi = 1: marks "consult the mask"
 constexpr uint32_t LUT_RAGGED_CODE = LUT_RAGGED_LO * 256u + LUT_RAGGED_NHI;     // lo * 256 + nhi
+constexpr uint32_t LUT_STRIDE_PLAIN = 65536u, LUT_STRIDE_SKEW = 66560u;
+constexpr uint32_t LUT_SKEW_IMAGE_OFS = 2u * LUT_STRIDE_PLAIN;                  // second image inside the table buffer
 
 // ---------------------------------------------------------------------------------------------
 // table construction: one warp per chroma pair
@@ -83,8 +87,14 @@ chroma_table_kernel(const uint32_t from, const uint32_t to, const uint32_t expec
   }
   if (lane == 0u)
   {
-    table[idx]          = (uint8_t)(count == 0u ? LUT_NEVER_LO : (rises == 1u ? lo : LUT_RAGGED_LO));
-    table[65536u + idx] = (uint8_t)(count == 0u ? LUT_NEVER_NHI : (rises == 1u ? 255u - hi : LUT_RAGGED_NHI));
+    const uint8_t eLo  = (uint8_t)(count == 0u ? LUT_NEVER_LO : (rises == 1u ? lo : LUT_RAGGED_LO));
+    const uint8_t eNhi = (uint8_t)(count == 0u ? LUT_NEVER_NHI : (rises == 1u ? 255u - hi : LUT_RAGGED_NHI));
+    table[idx]          = eLo;
+    table[65536u + idx] = eNhi;
+    // the same entries as the skewed shared-memory image of wo_lut_kernel<., true> (rows 260 bytes apart), copied verbatim
+    const uint32_t phys = idx + (idx >> 6);
+    table[LUT_SKEW_IMAGE_OFS + phys]                   = eLo;
+    table[LUT_SKEW_IMAGE_OFS + LUT_STRIDE_SKEW + phys] = eNhi;
   }
   if (lane < 8u)
   {
@@ -136,22 +146,30 @@ __device__ __forceinline__ uint32_t lut_pass_pair_masks(uint32_t word, uint32_t 
 
 // Persistent CTA: `groups` independent groups of `gthreads` threads, one frame per group at a time.
 // Inside a group the decomposition is sum_kernel's: a thread owns a 16-byte column chunk and walks down the rows.
-template <int STAGES>
+// SKEW: the table rows (one per V, 256 bytes apart) all start in the same shared-memory bank, so lanes whose chroma differs
+// only in V collide (a camera with chroma noise: ~5 values of V per warp -> 5-way conflicts on both lookups).  With SKEW
+// the entry of (U, V) lives at ci + (ci >> 6): rows 260 bytes apart (each starts one bank further), still injective
+// (U + (U >> 6) <= 258), one IMAD.HI more per pixel pair.
+template <bool SKEW>
+__device__ __forceinline__ uint32_t lut_phys(uint32_t ci) { return SKEW ? ci + __umulhi(ci, 1u << 26) : ci; }
+
+template <int STAGES, bool SKEW>
 __global__ void __launch_bounds__(1024, 1)
 wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
               const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
               const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi)
 {
+  constexpr uint32_t STRIDE = SKEW ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN;
   extern __shared__ __align__(16) uint8_t s_raw[];
-  uint8_t* const s_table = s_raw;                                                      // lo[65536], nhi[65536]
-  uint4* const s_ring = reinterpret_cast<uint4*>(s_raw + 131072);                     // [STAGES][groups * gthreads]
-  uint32_t* const s_red = reinterpret_cast<uint32_t*>(s_raw + 131072 + (size_t)STAGES * groups * gthreads * 16);   // [groups][32][4]
+  uint8_t* const s_table = s_raw;                                                      // lo[STRIDE], nhi[STRIDE]
+  uint4* const s_ring = reinterpret_cast<uint4*>(s_raw + 2u * STRIDE);                // [STAGES][groups * gthreads]
+  uint32_t* const s_red = reinterpret_cast<uint32_t*>(s_raw + 2u * STRIDE + (size_t)STAGES * groups * gthreads * 16);   // [groups][32][4]
 
   // the table, once per CTA
   {
-    const uint4* src = reinterpret_cast<const uint4*>(table);
+    const uint4* src = reinterpret_cast<const uint4*>(table + (SKEW ? LUT_SKEW_IMAGE_OFS : 0u));
     uint4* dst = reinterpret_cast<uint4*>(s_table);
-    for (int i = threadIdx.x; i < 131072 / 16; i += blockDim.x)
+    for (int i = threadIdx.x; i < (int)(2u * STRIDE / 16u); i += blockDim.x)
       dst[i] = __ldg(src + i);
   }
   __syncthreads();
@@ -204,10 +222,10 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
 #pragma unroll
       for (int k = 0; k < 4; ++k)
       {
-        const uint32_t ci = __byte_perm(wd[k], 0u, 0x4431);                    // U | V << 8
+        const uint32_t ci = lut_phys<SKEW>(__byte_perm(wd[k], 0u, 0x4431));    // U | V << 8 (skewed)
         uint32_t lo, nhi;
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(lo) : "r"(tbl + ci));
-        asm volatile("ld.shared.u8 %0, [%1+65536];" : "=r"(nhi) : "r"(tbl + ci));
+        asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(nhi) : "r"(tbl + ci), "n"(STRIDE));
         x[k] = lut_pass_pair(wd[k], lo, nhi);
         ragged |= (lo * 256u + nhi == LUT_RAGGED_CODE);
       }
@@ -217,7 +235,7 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
         for (int k = 0; k < 4; ++k)
         {
           const uint32_t ci = __byte_perm(wd[k], 0u, 0x4431);
-          if (s_table[ci] == LUT_RAGGED_LO && s_table[65536u + ci] == LUT_RAGGED_NHI)
+          if (s_table[lut_phys<SKEW>(ci)] == LUT_RAGGED_LO && s_table[STRIDE + lut_phys<SKEW>(ci)] == LUT_RAGGED_NHI)
             x[k] = lut_pass_pair_masks(wd[k], ci, masks);
         }
       }
@@ -283,16 +301,18 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
 // bitmap[(row/4) * (W/4) + col/4], bit (row%4)*4 + col%4 = det.  A thread produces the four metapixels under one
 // 16-pixel luma chunk: 4 rows x (16 luma + 16 chroma bytes), one 8-byte store.  Persistent CTAs (table in shared
 // memory, one per SM), blockDim = cpr * rows: `rows` metapixel rows of the batch at a time, no barrier needed.
+template <bool SKEW>
 __global__ void __launch_bounds__(768, 1)
 oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ table,
                      const uint32_t* __restrict__ masks, uint16_t* __restrict__ bitmaps,
                      const int numFrames, const int cpr, const int rows)
 {
+  constexpr uint32_t STRIDE = SKEW ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN;
   extern __shared__ __align__(16) uint8_t s_raw[];
   {
-    const uint4* src = reinterpret_cast<const uint4*>(table);
+    const uint4* src = reinterpret_cast<const uint4*>(table + (SKEW ? LUT_SKEW_IMAGE_OFS : 0u));
     uint4* dst = reinterpret_cast<uint4*>(s_raw);
-    for (int i = threadIdx.x; i < 131072 / 16; i += blockDim.x)
+    for (int i = threadIdx.x; i < (int)(2u * STRIDE / 16u); i += blockDim.x)
       dst[i] = __ldg(src + i);
   }
   __syncthreads();
@@ -329,10 +349,10 @@ oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const
       for (int k = 0; k < 8; ++k)
       {
         const uint32_t yy = __byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140);     // Y0 | Y1 << 16
-        const uint32_t ci = __byte_perm(Cw[k >> 1], 0u, (k & 1) ? 0x4423 : 0x4401);    // U | V << 8 (plane bytes: V U V U)
+        const uint32_t ci = lut_phys<SKEW>(__byte_perm(Cw[k >> 1], 0u, (k & 1) ? 0x4423 : 0x4401));   // U | V << 8 (plane bytes: V U V U)
         uint32_t lo, nhi;
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(lo) : "r"(tbl + ci));
-        asm volatile("ld.shared.u8 %0, [%1+65536];" : "=r"(nhi) : "r"(tbl + ci));
+        asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(nhi) : "r"(tbl + ci), "n"(STRIDE));
         x[k] = lut_pass_pair(yy, lo, nhi);
         ragged |= (lo * 256u + nhi == LUT_RAGGED_CODE);
       }
@@ -342,7 +362,7 @@ oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const
         for (int k = 0; k < 8; ++k)
         {
           const uint32_t ci = __byte_perm(Cw[k >> 1], 0u, (k & 1) ? 0x4423 : 0x4401);
-          if (s_raw[ci] == LUT_RAGGED_LO && s_raw[65536u + ci] == LUT_RAGGED_NHI)
+          if (s_raw[lut_phys<SKEW>(ci)] == LUT_RAGGED_LO && s_raw[STRIDE + lut_phys<SKEW>(ci)] == LUT_RAGGED_NHI)
             x[k] = lut_pass_pair_masks(__byte_perm(L[k >> 1], 0u, (k & 1) ? 0x4342 : 0x4140), ci, masks);
         }
       }
@@ -375,10 +395,16 @@ cudaError_t launch_oo_bitmap_lut(const Geometry& g, int numFrames, const uint8_t
   const long long units = (long long)numFrames * (g.height / 4);
   long long grid = (units + rows - 1) / rows;
   if (grid > smCount) grid = smCount;
-  cudaError_t e = cudaFuncSetAttribute(oo_bitmap_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+  const bool skew = g_lutSkew != 0;
+  const int smem = (int)(2u * (skew ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN));
+  cudaError_t e = skew ? cudaFuncSetAttribute(oo_bitmap_lut_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                       : cudaFuncSetAttribute(oo_bitmap_lut_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess)
     return e;
-  oo_bitmap_lut_kernel<<<(unsigned)grid, threads, 131072, stream>>>(g, frames, table, masks, bitmaps, numFrames, cpr, rows);
+  if (skew)
+    oo_bitmap_lut_kernel<true><<<(unsigned)grid, threads, smem, stream>>>(g, frames, table, masks, bitmaps, numFrames, cpr, rows);
+  else
+    oo_bitmap_lut_kernel<false><<<(unsigned)grid, threads, smem, stream>>>(g, frames, table, masks, bitmaps, numFrames, cpr, rows);
   ++g_launches_lut;
   return cudaGetLastError();
 }
@@ -438,7 +464,9 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
   int groups = 1024 / gthreads;
   if (groups > 15) groups = 15;                           // named barriers 1..15
   // shared memory: table + ring + reduction scratch
-  auto smem_for = [&](int ng) { return (size_t)131072 + (size_t)STAGES * ng * gthreads * 16 + (size_t)ng * 128 * 4; };
+  const bool skew = g_lutSkew != 0;
+  const size_t tableBytes = 2u * (skew ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN);
+  auto smem_for = [&](int ng) { return tableBytes + (size_t)STAGES * ng * gthreads * 16 + (size_t)ng * 128 * 4; };
   while (groups > 1 && smem_for(groups) > 220 * 1024) --groups;
   if (smem_for(groups) > 227 * 1024)
     return cudaErrorInvalidValue;
@@ -446,10 +474,14 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
   int grid = (numFrames + groups - 1) / groups;
   if (grid > smCount) grid = smCount;
   const size_t smem = smem_for(groups);
-  cudaError_t e = cudaFuncSetAttribute(wo_lut_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = skew ? cudaFuncSetAttribute(wo_lut_kernel<STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(wo_lut_kernel<STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
-  wo_lut_kernel<STAGES><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi);
+  if (skew)
+    wo_lut_kernel<STAGES, true><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi);
+  else
+    wo_lut_kernel<STAGES, false><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi);
   ++g_launches_lut;
   return cudaGetLastError();
 }
