@@ -67,7 +67,10 @@ def main():
             d_out = torch.zeros((n, rec), dtype=torch.uint8, device=dev)
             codec = open_sensor(kind, w, h)
             if kind == "oo":
-                ia = xdm.ObjInArgsAlg(1, 0, 20, 80, 20, 50, 30, 0)
+                # OOARGS=wide: a range that the blob / speck frames actually fall into (the default one finds nothing in
+                # them, i.e. measures the walk over empty bitmaps)
+                ia = (xdm.ObjInArgsAlg(1, 0, 25, 75, 25, 60, 40, 0) if os.environ.get("OOARGS") == "wide"
+                      else xdm.ObjInArgsAlg(1, 0, 20, 80, 20, 50, 30, 0))
             elif kind == "om":
                 ia = xdm.MxnInArgsAlg(gm, gn)
             else:
