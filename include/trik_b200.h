@@ -267,6 +267,31 @@ typedef struct TRIKB200_Ingest {
 } TRIKB200_Ingest;
 XDAS_Int32 trikb200_ingestRgb565(const TRIKB200_Ingest* ingest);
 
+/* ov7670/edge_line_sensor as a batch operation: targetX / targetY / targetSize of
+ * ov7670/edge_line_sensor/include/internal/cv_ball_detector_seqpass.hpp (Sobel 3x3 of the luma plane, threshold 50, centroid
+ * column of the edge pixels in columns 16 .. width-16; :176-205, :386-414) for every frame, written as
+ * TRIKB200_TargetOutArgsAlg records (the six detect* fields are written as 0; the reference leaves them alone).
+ * Only the luma plane is read: frames may be whole YUV422P frames (frameStride = 2 * lineLength * height) or bare planes.
+ * PARITY UNPINNED: the sensor's Sobel / threshold kernels are TI IMGLIB (closed, absent from the reference tree); they
+ * are taken from TI's published natural-C models (oracle/imglib_open.c).  Not a codec handle: the reference's preview for
+ * this sensor goes through a third IMGLIB kernel (IMG_ycbcr422pl_to_rgb565) and is not produced.
+ * width % 32 == 0, 32 <= width <= 1040, height % 4 == 0, lineLength >= width (the reference itself ignores inputLineLength
+ * in its Sobel call, i.e. assumes lineLength == width). */
+typedef struct TRIKB200_EdgeLineBatch {
+    XDAS_Int32  size;            /* sizeof(TRIKB200_EdgeLineBatch) */
+    XDAS_Int32  numFrames;
+    XDAS_Int32  width, height;
+    XDAS_Int32  lineLength;      /* bytes per luma row */
+    XDAS_Int32  framesMem;       /* TRIKB200_MEM_* */
+    XDAS_Int32  outArgsMem;      /* TRIKB200_MEM_* */
+    XDAS_Int32  outArgsStride;   /* bytes between records, >= sizeof(TRIKB200_TargetOutArgsAlg) */
+    const void* frames;          /* frame i at frames + i * frameStride */
+    int64_t     frameStride;
+    void*       outArgsAlg;
+    void*       stream;          /* cudaStream_t, NULL = the default stream; device memory on both sides: enqueued only */
+} TRIKB200_EdgeLineBatch;
+XDAS_Int32 trikb200_edgeLineBatch(const TRIKB200_EdgeLineBatch* batch);
+
 /* wait for everything enqueued on the handle (TRIKB200_BATCH_ASYNC) */
 XDAS_Int32 trikb200_synchronize(IVIDTRANSCODE_Handle handle);
 

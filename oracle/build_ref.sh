@@ -1,7 +1,9 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE (oracle/): build oracle/_ref/libtrikref_<kind>.so from the reference's own
 # sources where they lie under $REF (default /root/reference).  See oracle/Makefile for the why
-# of every flag.  Usage: build_ref.sh <wo|wl|oo|ol|om> [more kinds...]
+# of every flag.  Usage: build_ref.sh <wo|wl|oo|ol|om|oe> [more kinds...]
+# oe = ov7670/edge_line_sensor: its Sobel / threshold / colour-conversion kernels are TI IMGLIB (closed, un-vendored);
+# the reference's own sensor code is compiled against the open restatement oracle/imglib_open.c (parity unpinned there).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${REF:-/root/reference}"
@@ -14,16 +16,17 @@ INC="-I$HERE/stubs -I$HERE/../include"
 CXXFLAGS="-std=gnu++11 $OPT -fPIC -DNDEBUG=1 -fno-strict-aliasing -Dtypeof=__typeof__ -w"
 CFLAGS="$OPT -fPIC -DNDEBUG=1 -w"
 
-declare -A CLASSES=([wo]=BallDetector [wl]=LineDetector [oo]=BallDetector [ol]=LineDetector [om]=BallDetector)
+declare -A CLASSES=([wo]=BallDetector [wl]=LineDetector [oo]=BallDetector [ol]=LineDetector [om]=BallDetector [oe]=BallDetector)
 declare -A FORMATS=([wo]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422 [wl]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422
                     [oo]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P [ol]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P
-                    [om]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P)
+                    [om]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P [oe]=TRIK_VIDTRANSCODE_CV_VIDEO_FORMAT_YUV422P)
 declare -A DIRS=(
   [wo]="$REF/trik/webcam/object_sensor"
   [wl]="$REF/trik/webcam/line_sensor"
   [oo]="$REF/trik/ov7670/object_sensor"
   [ol]="$REF/trik/ov7670/line_sensor"
   [om]="$REF/trik/ov7670/mxn_sensor"
+  [oe]="$REF/trik/ov7670/edge_line_sensor"
 )
 
 mkdir -p "$OUT"
@@ -45,13 +48,19 @@ for kind in "$@"; do
       > "$tmp/patch/internal/cv_bitmap_builder_reference.hpp"
     extra="-I$tmp/patch"
   fi
+  objs=""
+  if [ "$kind" = "oe" ]; then
+    extra="-I$HERE/stubs_imglib -DTRIKREF_NO_PIXEL_PROBES=1"
+    $CC $CFLAGS -Wall -c "$HERE/imglib_open.c" -o "$tmp/imglib.o"
+    objs="$tmp/imglib.o"
+  fi
   # ref_unit.cpp #includes the reference's src/vidtranscode_cv.cpp verbatim and adds the pixel probes
   $CXX $CXXFLAGS $extra -I"$dir" -I"$dir/include" $INC \
        -DTRIKREF_SRC="\"$dir/src/vidtranscode_cv.cpp\"" -DTRIKREF_CLASS="${CLASSES[$kind]}" -DTRIKREF_FORMAT="${FORMATS[$kind]}" \
        -c "$HERE/ref_unit.cpp" -o "$tmp/cv.o"
   $CC  $CFLAGS -I"$dir" -I"$dir/include" $INC -c "$dir/src/vidtranscode_cv_fxns.c" -o "$tmp/fxns.o"
   $CC  $CFLAGS -Wall -I"$dir" -I"$dir/include" $INC -c "$HERE/ref_driver.c" -o "$tmp/drv.o"
-  $CXX $OPT -shared -o "$OUT/libtrikref_${kind}${SUFFIX}.so" "$tmp/cv.o" "$tmp/fxns.o" "$tmp/drv.o" -Wl,--wrap=time -lm
+  $CXX $OPT -shared -o "$OUT/libtrikref_${kind}${SUFFIX}.so" "$tmp/cv.o" "$tmp/fxns.o" "$tmp/drv.o" $objs -Wl,--wrap=time -lm
   rm -rf "$tmp"
   trap - EXIT
   echo "built $OUT/libtrikref_${kind}${SUFFIX}.so"

@@ -18,7 +18,10 @@ KINDS = ("wo", "wl", "oo", "ol", "om")
 FORMAT_YUV422 = 0x100 + 4
 FORMAT_YUV422P = 0x100 + 5
 FORMAT_OF = {"wo": FORMAT_YUV422, "wl": FORMAT_YUV422, "oo": FORMAT_YUV422P,
-             "ol": FORMAT_YUV422P, "om": FORMAT_YUV422P}
+             "ol": FORMAT_YUV422P, "om": FORMAT_YUV422P, "oe": FORMAT_YUV422P}
+# "oe" = ov7670/edge_line_sensor: only as a RefSensor (the reference's own sensor code built against
+# the open IMGLIB restatement oracle/imglib_open.c) and through edge_line() of the C restatement -- not an OracleSensor kind
+REF_KINDS = KINDS + ("oe",)
 
 
 class RangeInArgs(C.Structure):
@@ -68,8 +71,8 @@ class MxnOutArgs(C.Structure):
     _fields_ = [("outColor", C.c_int32 * 100)]
 
 
-IN_ARGS = {"wo": RangeInArgs, "wl": RangeInArgs, "ol": RangeInArgs, "oo": ObjInArgs, "om": MxnInArgs}
-OUT_ARGS = {"wo": TargetOutArgs, "wl": TargetOutArgs, "ol": TargetOutArgs, "oo": ObjOutArgs, "om": MxnOutArgs}
+IN_ARGS = {"wo": RangeInArgs, "wl": RangeInArgs, "ol": RangeInArgs, "oo": ObjInArgs, "om": MxnInArgs, "oe": RangeInArgs}
+OUT_ARGS = {"wo": TargetOutArgs, "wl": TargetOutArgs, "ol": TargetOutArgs, "oo": ObjOutArgs, "om": MxnOutArgs, "oe": TargetOutArgs}
 
 
 def ref_available(kind="wo"):
@@ -92,7 +95,7 @@ class RefSensor:
     """
 
     def __init__(self, kind, suffix=""):
-        assert kind in KINDS
+        assert kind in REF_KINDS
         path = os.path.join(REF_DIR, "libtrikref_%s%s.so" % (kind, suffix))
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (build with: make -C oracle ref)")
@@ -172,6 +175,7 @@ def port_lib():
         lib.trik_oracle_rgb888_to_hsv_range.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         lib.trik_oracle_srand.argtypes = [C.c_void_p, C.c_uint]
         lib.trik_oracle_rand.argtypes = [C.c_void_p]
+        lib.trik_oracle_edge_line.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _port = lib
     return _port
 
@@ -219,3 +223,11 @@ class OracleSensor:
 
 def struct_bytes(s):
     return bytes(memoryview(s))
+
+
+def edge_line(frame, w, h, line_length=None):
+    """ov7670/edge_line_sensor restated (trik_oracle_edge_line): returns a TargetOutArgs with targetX / targetY / targetSize."""
+    assert frame.dtype == np.uint8 and frame.flags["C_CONTIGUOUS"] and frame.nbytes >= (line_length or w) * h
+    out = TargetOutArgs()
+    port_lib().trik_oracle_edge_line(frame.ctypes.data, w, h, line_length or w, C.byref(out))
+    return out

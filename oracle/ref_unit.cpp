@@ -33,6 +33,10 @@ typedef trik::cv::TRIKREF_CLASS<TRIKREF_FORMAT, TRIK_VIDTRANSCODE_CV_VIDEO_FORMA
 
 /* out[i] = 0x00RRGGBB of the FIRST pixel of the YUYV word built from index first+i = Y | U<<8 | V<<16;
  * the second pixel of the word carries luma 255-Y and is checked to land in the high word. */
+#ifdef TRIKREF_NO_PIXEL_PROBES   /* edge_line_sensor: no HSV pipeline in this class */
+extern "C" int trikref_probe_yuv2rgb(uint32_t, uint32_t, uint32_t*, uint32_t*) { return -1; }
+extern "C" int trikref_probe_rgb2hsv(uint32_t, uint32_t, uint32_t*) { return -1; }
+#else
 extern "C" int trikref_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, uint32_t* outSecond)
 {
   for (uint32_t i = 0; i < count; ++i)
@@ -58,3 +62,4 @@ extern "C" int trikref_probe_rgb2hsv(uint32_t first, uint32_t count, uint32_t* o
     out[i] = TrikRefAlgorithm::convertRgb888ToHsv(first + i);
   return 0;
 }
+#endif

@@ -976,3 +976,57 @@ int trik_oracle_rand(uint32_t* st)
   st[31] = f; st[32] = r;
   return (int)(val >> 1);
 }
+
+/* =============================================================================================
+ * ov7670/edge_line_sensor
+ *   convertImageYuyvToRgb: include/internal/cv_ball_detector_seqpass.hpp:151-205 (Sobel, threshold, counting loop)
+ *   run tail:              :386-414
+ * The Sobel and threshold kernels are TI IMGLIB (closed, absent): restated in oracle/imglib_open.c, PARITY UNPINNED.
+ * The reference hands the input to IMG_sobel_3x3_8 as a dense width x height array (it ignores inputLineLength there);
+ * here rows are lineLength bytes apart and are gathered densely first, which is the same thing when lineLength == width.
+ * The reference's work buffer s_y is a zero-initialised static whose last two rows (and first byte) the Sobel never
+ * writes, so they stay 0 for ever: calloc reproduces that.
+ * ============================================================================================= */
+void IMG_sobel_3x3_8(const unsigned char* in, unsigned char* out, short cols, short rows);
+void IMG_thr_gt2max_8(const unsigned char* in_data, unsigned char* out_data, short cols, short rows, unsigned char threshold);
+
+void trik_oracle_edge_line(const uint8_t* frame, int width, int height, int lineLength, void* outArgsAlg)
+{
+  trik_oracle_target_out* o = (trik_oracle_target_out*)outArgsAlg;
+  const size_t n = (size_t)width * (size_t)height;
+  uint8_t* in = (uint8_t*)malloc(n ? n : 1);
+  uint8_t* sy = (uint8_t*)calloc(n ? n : 1, 1);
+  int32_t tx = 0;
+  uint32_t points = 0;
+  int r, c;
+  o->targetX = 0; o->targetY = 0; o->targetSize = 0;
+  if (!in || !sy || width <= 0 || height <= 0) { free(in); free(sy); return; }
+  for (r = 0; r < height; ++r)
+    memcpy(in + (size_t)r * width, frame + (size_t)r * lineLength, (size_t)width);
+  IMG_sobel_3x3_8(in, sy, (short)width, (short)height);                       /* :176-178 */
+  IMG_thr_gt2max_8(sy, sy, (short)width, (short)height, 50);                  /* :180-182 */
+  for (r = 0; r < height; ++r)                                                /* :186-205 */
+  {
+    uint16_t perRow = 0, colSum = 0;                                          /* uint16_t in the reference: sums wrap */
+    for (c = 0; c < width; ++c)
+      if (c > 15 && c < width - 15)
+      {
+        const int det = sy[(size_t)r * width + c] == 0xFF;
+        perRow = (uint16_t)(perRow + det);
+        colSum = (uint16_t)(colSum + (det ? c : 0));
+      }
+    tx += colSum;
+    points += perRow;
+  }
+  if (points > 0)                                                             /* :388-403; m_targetY is never added to */
+  {
+    const int32_t targetX = (int32_t)((uint32_t)tx / points);
+    const int32_t targetY = 0;
+    const uint32_t radius = (uint32_t)ceilf(sqrtf((float)points / 3.1415927f));
+    o->targetX = (int8_t)(((targetX - (int32_t)width / 2) * 100 * 2) / (int32_t)width);
+    o->targetY = (int8_t)(((targetY - (int32_t)height / 2) * 100 * 2) / (int32_t)height);
+    o->targetSize = (uint8_t)((uint32_t)(radius * 100 * 4) / (uint32_t)(width + height));
+  }
+  free(in);
+  free(sy);
+}

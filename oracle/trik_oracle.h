@@ -93,6 +93,12 @@ int trik_oracle_last_flags(const trik_oracle_sensor* s);
 /* whole-image HSV (0x00VVSSHH per pixel) of the last run, for kernel debugging */
 const uint32_t* trik_oracle_last_hsv(const trik_oracle_sensor* s);
 
+/* ov7670/edge_line_sensor, restated: Sobel 3x3 of the luma plane through the open IMGLIB restatement
+ * (oracle/imglib_open.c -- the real IMGLIB is closed and absent: PARITY UNPINNED for those kernels), threshold 50, then the
+ * sensor's own counting loop and tail (include/internal/cv_ball_detector_seqpass.hpp:186-205, :369-420).
+ * frame: luma plane of height rows, lineLength bytes apart; out: trik_oracle_target_out (targetX, targetY, targetSize). */
+void trik_oracle_edge_line(const uint8_t* frame, int width, int height, int lineLength, void* outArgsAlg);
+
 /* glibc TYPE_3 rand() restated (used by tests to pin the product's private generator) */
 void trik_oracle_srand(uint32_t* state34, unsigned seed);
 int  trik_oracle_rand(uint32_t* state34);

@@ -1,6 +1,7 @@
 """Pin the oracle (oracle/trik_oracle.c) against the reference's own sources built for the host
 (oracle/_ref/libtrikref_*.so).  CPU only; skipped where the reference build is absent."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -144,3 +145,34 @@ def test_glibc_rand_restatement():
         lib.trik_oracle_srand(st, C.c_uint(seed))
         for _ in range(2000):
             assert libc.rand() == lib.trik_oracle_rand(st)
+
+
+# ---------------------------------------------------------------------------------------------
+# ov7670/edge_line_sensor: the restatement of the whole sensor against the reference's own sensor code
+# built with the open IMGLIB restatement (oracle/imglib_open.c) -- the IMGLIB arithmetic itself stays unpinned
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(ref.__file__), "_ref", "libtrikref_oe.so")),
+                    reason="oracle/_ref/libtrikref_oe.so not built")
+@pytest.mark.parametrize("size", [(320, 240), (160, 120), (64, 8), (320, 100)])
+def test_edge_line_restatement_equals_reference_sensor_code(size):
+    w, h = size
+    rs = ref.RefSensor("oe")
+    # the reference's work buffer is a file-scope static that is never cleared: rows the Sobel does not write keep what an
+    # earlier geometry left there.  An all-zero frame at the largest geometry wipes it, as in a fresh process.
+    assert rs.setup(320, 240)[0] == 0
+    zero = ref.aligned_bytes(3 * 320 * 240)
+    zero[:] = 0
+    assert rs.process(zero, ref.RangeInArgs(0, 359, 0, 100, 0, 100, 0), num_bytes=2 * 320 * 240)[0] == 0
+    assert rs.setup(w, h)[0] == 0
+    fams = [("scene", s) for s in range(8)] + [("noise", 0), ("blobs", 1), ("camera", 2)] + [(e, 0) for e in synth.EDGE_CASES]
+    buf = ref.aligned_bytes(3 * w * h)          # the reference reads 2*W*H bytes from the chroma offset (:160-168)
+    seen = set()
+    for fam, seed in fams:
+        f = synth.make_frame(fam, seed, w, h, "yuv422p")
+        buf[:] = 0
+        buf[:f.size] = f
+        ret, out, _ = rs.process(buf, ref.RangeInArgs(0, 359, 0, 100, 0, 100, 0), num_bytes=2 * w * h)
+        e = ref.edge_line(f, w, h)
+        assert ret == 0 and (out.targetX, out.targetY, out.targetSize) == (e.targetX, e.targetY, e.targetSize), (size, fam, seed)
+        seen.add((e.targetX, e.targetY, e.targetSize))
+    assert len(seen) > 3

@@ -1582,6 +1582,58 @@ XDAS_Int32 trikb200_ingestRgb565(const TRIKB200_Ingest* d)
   return IVIDTRANSCODE_EOK;
 }
 
+XDAS_Int32 trikb200_edgeLineBatch(const TRIKB200_EdgeLineBatch* d)
+{
+  if (!d || d->size != (XDAS_Int32)sizeof(TRIKB200_EdgeLineBatch) || d->numFrames < 0 || !d->frames || !d->outArgsAlg
+      || d->outArgsStride < (XDAS_Int32)sizeof(TRIKB200_TargetOutArgsAlg))
+  {
+    set_error("edgeLineBatch: bad descriptor");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if (d->numFrames == 0)
+    return IVIDTRANSCODE_EOK;
+  cudaStream_t s = static_cast<cudaStream_t>(d->stream);
+  const bool srcHost = d->framesMem != TRIKB200_MEM_DEVICE, dstHost = d->outArgsMem != TRIKB200_MEM_DEVICE;
+  const size_t plane = (size_t)d->lineLength * d->height;
+  const uint8_t* frames = static_cast<const uint8_t*>(d->frames);
+  long long frameStride = d->frameStride;
+  uint8_t *dFrames = nullptr, *dOut = nullptr;
+  uint8_t* out = static_cast<uint8_t*>(d->outArgsAlg);
+  int outStride = d->outArgsStride;
+  cudaError_t e = cudaSuccess;
+  if (srcHost)
+  {
+    e = cudaMalloc(&dFrames, plane * d->numFrames);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(dFrames, plane, frames, (size_t)d->frameStride, plane, (size_t)d->numFrames, cudaMemcpyHostToDevice, s);
+    frames = dFrames; frameStride = (long long)plane;
+  }
+  if (e == cudaSuccess && dstHost)
+  {
+    e = cudaMalloc(&dOut, sizeof(TargetOut) * (size_t)d->numFrames);
+    out = dOut; outStride = (int)sizeof(TargetOut);
+  }
+  if (e == cudaSuccess)
+    e = launch_edge_line(frames, frameStride, d->lineLength, d->width, d->height, d->numFrames, reinterpret_cast<TargetOut*>(out), outStride, s);
+  if (e == cudaSuccess && dstHost)
+    e = cudaMemcpy2DAsync(d->outArgsAlg, (size_t)d->outArgsStride, dOut, sizeof(TargetOut), sizeof(TargetOut), (size_t)d->numFrames,
+                          cudaMemcpyDeviceToHost, s);
+  if (srcHost || dstHost)
+  {
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
+    cudaFree(dFrames);
+    cudaFree(dOut);
+  }
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    set_error("edgeLineBatch", e);
+    return IVIDTRANSCODE_EFAIL;
+  }
+  return IVIDTRANSCODE_EOK;
+}
+
 XDAS_Int32 trikb200_probeLut(const TRIKB200_RangeInArgsAlg* inArgsAlg, uint64_t stats[5])
 {
   Geometry g{};

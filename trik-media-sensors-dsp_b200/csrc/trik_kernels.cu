@@ -68,7 +68,8 @@ extern std::atomic<long long> g_launches_lut;
 extern std::atomic<long long> g_launches_anneal;
 extern std::atomic<long long> g_launches_omtab;
 extern std::atomic<long long> g_launches_ingest;
-long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line + g_launches_lut + g_launches_anneal + g_launches_omtab + g_launches_ingest; }
+extern std::atomic<long long> g_launches_edge;
+long long launch_count() { return g_launches + g_launches_grid + g_launches_detect + g_launches_preview + g_launches_line + g_launches_lut + g_launches_anneal + g_launches_omtab + g_launches_ingest + g_launches_edge; }
 
 // ---------------------------------------------------------------------------------------------
 // per-pair work

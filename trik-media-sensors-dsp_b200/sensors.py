@@ -60,6 +60,8 @@ def lib():
         l.trikb200_probeLut.argtypes = [C.c_void_p, C.c_void_p]
         l.trikb200_ingestRgb565.argtypes = [C.POINTER(xdm.Ingest)]
         l.trikb200_ingestRgb565.restype = C.c_int32
+        l.trikb200_edgeLineBatch.argtypes = [C.POINTER(xdm.EdgeLineBatch)]
+        l.trikb200_edgeLineBatch.restype = C.c_int32
         for f in ("trikb200_sizeofInArgsAlg", "trikb200_sizeofOutArgsAlg", "trikb200_sizeofInArgs",
                   "trikb200_sizeofOutArgs"):
             getattr(l, f).argtypes = [C.c_int32]
@@ -84,6 +86,21 @@ def ingest_rgb565(src, width, height, pixel_format=xdm.PIXEL_RGB565, src_line_le
     d.dst, d.dstStride = out.ctypes.data, out.strides[0]
     ret = lib().trikb200_ingestRgb565(C.byref(d))
     return ret, out
+
+
+def edge_line_batch(frames, width, height, line_length=None):
+    """Host-memory form of trikb200_edgeLineBatch: frames (n, >= line_length * height) uint8 whose first plane is the luma
+    -> (ret, TargetOutArgsAlg array)."""
+    assert frames.dtype == np.uint8 and frames.ndim == 2 and frames.flags["C_CONTIGUOUS"]
+    n = frames.shape[0]
+    outs = (xdm.TargetOutArgsAlg * n)()
+    d = xdm.EdgeLineBatch()
+    d.size = C.sizeof(d)
+    d.numFrames, d.width, d.height, d.lineLength = n, width, height, width if line_length is None else line_length
+    d.framesMem, d.outArgsMem, d.outArgsStride = xdm.MEM_HOST, xdm.MEM_HOST, C.sizeof(xdm.TargetOutArgsAlg)
+    d.frames, d.frameStride, d.outArgsAlg = frames.ctypes.data, frames.strides[0], C.addressof(outs)
+    ret = lib().trikb200_edgeLineBatch(C.byref(d))
+    return ret, outs
 
 
 def last_error():

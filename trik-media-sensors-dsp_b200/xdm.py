@@ -210,6 +210,13 @@ class Ingest(C.Structure):
 PIXEL_RGB565, PIXEL_RGB565X = 0, 1
 
 
+class EdgeLineBatch(C.Structure):
+    """TRIKB200_EdgeLineBatch (include/trik_b200.h): ov7670/edge_line_sensor as a batch operation."""
+    _fields_ = [("size", C.c_int32), ("numFrames", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("lineLength", C.c_int32), ("framesMem", C.c_int32), ("outArgsMem", C.c_int32), ("outArgsStride", C.c_int32),
+                ("frames", C.c_void_p), ("frameStride", C.c_int64), ("outArgsAlg", C.c_void_p), ("stream", C.c_void_p)]
+
+
 class MixedEntry(C.Structure):
     _fields_ = [("handle", C.c_void_p), ("frame", C.c_void_p), ("inArgsAlg", C.c_void_p), ("outArgsAlg", C.c_void_p),
                 ("seed", C.c_int64)]
