@@ -330,6 +330,9 @@ void trikb200_setMxnTableMode(XDAS_Int32 mode);
  * instead of 256 bytes apart): no bank conflicts when the chroma of neighbouring pixels differs by a little (camera noise),
  * for one more instruction per pixel pair (+60..75 % on such frames, -4 % on frames with noise-free chroma); 0 = plain rows */
 void trikb200_setLutSkew(XDAS_Int32 on);
+/* tuning knob: edge-line kernel, 0 = packed four-pixels-per-thread form (default, needs 4-byte aligned rows), 1 = one thread
+ * per column (first version) */
+void trikb200_setEdgeLineVariant(XDAS_Int32 variant);
 /* tuning knob: target CTA size of the mxn table kernel, 0 = default */
 void trikb200_setMxnTableThreads(XDAS_Int32 threads);
 /* tuning knob: synchronous host-memory calls of up to this many frame bytes (default 1 MiB; process() is one frame)

@@ -28,12 +28,18 @@ def rec(o):
 def test_edge_line_matches_the_restatement(size):
     w, h = size
     frames = np.stack([synth.make_frame(f, s, w, h, "yuv422p") for f, s in FAMS])
-    ret, outs = sensors.edge_line_batch(frames, w, h)
-    assert ret == 0, sensors.last_error()
-    for i in range(frames.shape[0]):
-        assert rec(outs[i]) == rec(oracle.edge_line(frames[i], w, h)), (size, FAMS[i])
+    want = [rec(oracle.edge_line(frames[i], w, h)) for i in range(frames.shape[0])]
+    try:
+        for variant in (0, 1):                                 # packed four-pixel kernel, one-thread-per-column kernel
+            lib().trikb200_setEdgeLineVariant(variant)
+            ret, outs = sensors.edge_line_batch(frames, w, h)
+            assert ret == 0, sensors.last_error()
+            for i in range(frames.shape[0]):
+                assert rec(outs[i]) == want[i], (size, variant, FAMS[i])
+    finally:
+        lib().trikb200_setEdgeLineVariant(0)
     if w >= 160:
-        assert len({rec(o) for o in outs}) > 4                 # the vectors do tell frames apart
+        assert len(set(want)) > 4                              # the vectors do tell frames apart
 
 
 @requires_ref
@@ -64,10 +70,14 @@ def test_row_sums_wrap_like_the_reference_uint16():
     w, h = 640, 16
     y = np.repeat(((np.arange(h) % 4 < 2) * 255).astype(np.uint8)[:, None], w, axis=1)          # stripes two rows thick: every pixel an edge
     frame = synth.pack(y, np.full((h, w // 2), 128, np.uint8), np.full((h, w // 2), 128, np.uint8), "yuv422p")[None, :]
-    ret, outs = sensors.edge_line_batch(frame, w, h)
-    assert ret == 0
     want = oracle.edge_line(frame[0], w, h)
-    assert rec(outs[0]) == rec(want)
+    try:
+        for variant in (0, 1):
+            lib().trikb200_setEdgeLineVariant(variant)
+            ret, outs = sensors.edge_line_batch(frame, w, h)
+            assert ret == 0 and rec(outs[0]) == rec(want), variant
+    finally:
+        lib().trikb200_setEdgeLineVariant(0)
     assert rec(want)[0] != 0                                   # with exact sums the centroid would be the middle (0)
 
 

@@ -1495,6 +1495,7 @@ void trikb200_setOverlapLaunch(XDAS_Int32 on) { set_overlap_launch(on); }
 void trikb200_setLutMode(XDAS_Int32 mode) { g_lutMode = mode; }
 void trikb200_setMxnTableMode(XDAS_Int32 mode) { g_mxnTableMode = mode; }
 void trikb200_setLutSkew(XDAS_Int32 on) { set_lut_skew(on); }
+void trikb200_setEdgeLineVariant(XDAS_Int32 variant) { set_edge_variant(variant); }
 void trikb200_setMxnTableThreads(XDAS_Int32 threads) { set_om_table_threads(threads); }
 void trikb200_setZeroCopyBytes(XDAS_Int32 bytes) { g_zeroCopyBytes = bytes; }
 void trikb200_setFramesPerCta(XDAS_Int32 n) { set_frames_per_cta(n); }

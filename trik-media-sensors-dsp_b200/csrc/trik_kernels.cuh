@@ -136,6 +136,7 @@ cudaError_t launch_ingest_rgb565(const uint8_t* src, long long srcStride, int sr
 // ov7670/edge_line_sensor (trik_kernels_edge.cu): out record i at out + i * outStride bytes
 cudaError_t launch_edge_line(const uint8_t* frames, long long frameStride, int lineLength, int width, int height,
                              int numFrames, TargetOut* out, int outStride, cudaStream_t stream);
+void set_edge_variant(int v);
 long long launch_count();
 
 } // namespace trikb200

@@ -52,6 +52,7 @@ def lib():
         l.trikb200_setLutMode.argtypes = [C.c_int32]
         l.trikb200_setMxnTableMode.argtypes = [C.c_int32]
         l.trikb200_setLutSkew.argtypes = [C.c_int32]
+        l.trikb200_setEdgeLineVariant.argtypes = [C.c_int32]
         l.trikb200_setMxnTableThreads.argtypes = [C.c_int32]
         l.trikb200_setZeroCopyBytes.argtypes = [C.c_int32]
         l.trikb200_setFramesPerCta.argtypes = [C.c_int32]
