@@ -128,7 +128,8 @@ __device__ __forceinline__ uint32_t edge_hits2(uint32_t A0, uint32_t A2, uint32_
   const uint32_t Vb = D0 + 2u * D1 + D2;                        // three biased differences + one more: bias 4 * 256
   const uint32_t aH = __vmaxu2(Hb, 0x08000800u - Hb);
   const uint32_t aV = __vmaxu2(Vb, 0x08000800u - Vb);
-  return __vcmpgtu2(aH + aV, 0x08320832u) & 0x00010001u;        // 2048 + 50 = 0x832
+  // lane sum = 2048 + |H| + |V| <= 4088: adding 32768 - 2099 carries into bit 15 exactly when |H| + |V| > 50
+  return ((aH + aV + 0x77CD77CDu) >> 15) & 0x00010001u;
 }
 
 template <bool WRAP>
@@ -141,9 +142,11 @@ edge_line4_kernel(const uint8_t* __restrict__ frames, const long long frameStrid
   const int frame = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = (int)(blockDim.x >> 5);
   const int grp = t / wpr, wi = t - grp * wpr;              // wpr is a multiple of 32: a warp never straddles two bands
-  const int j = 4 + wi;                                     // luma word index: columns 4j .. 4j+3, first counted word is 4
+  // a warp covers 30 words; its lanes 0 and 31 only carry the words next to them (no extra loads, no special cases)
+  const int j = 4 + (wi >> 5) * 30 + lane - 1;              // luma word index: columns 4j .. 4j+3, first counted word is 4
   const int lastWord = (W - 16) >> 2;                       // holds column W-16, its only counted one
-  const bool live = grp < groups && j <= lastWord;
+  const bool loads = grp < groups && j >= 3 && 4 * j < W;
+  const bool live = grp < groups && lane != 0 && lane != 31 && j <= lastWord;
   const uint8_t* base = frames + (long long)frame * frameStride;
   if (WRAP)
   {
@@ -158,11 +161,9 @@ edge_line4_kernel(const uint8_t* __restrict__ frames, const long long frameStrid
   auto load_row = [&](int k, uint32_t& Alo, uint32_t& Ahi, uint32_t& Dlo, uint32_t& Dhi)
   {
     const uint32_t* rowp = reinterpret_cast<const uint32_t*>(base + (size_t)k * lineLength);
-    const uint32_t m = live ? __ldg(rowp + j) : 0u;
-    uint32_t lw = __shfl_up_sync(0xFFFFFFFFu, m, 1);
-    uint32_t rw = __shfl_down_sync(0xFFFFFFFFu, m, 1);
-    if (lane == 0) lw = live ? __ldg(rowp + j - 1) : 0u;                       // j >= 4
-    if (lane == 31) rw = (live && 4 * (j + 1) < W) ? __ldg(rowp + j + 1) : 0u;
+    const uint32_t m = loads ? __ldg(rowp + j) : 0u;
+    const uint32_t lw = __shfl_up_sync(0xFFFFFFFFu, m, 1);
+    const uint32_t rw = __shfl_down_sync(0xFFFFFFFFu, m, 1);
     const uint32_t l = __byte_perm(lw, m, 0x6543);            // bytes of columns 4j-1 .. 4j+2
     const uint32_t r = __byte_perm(m, rw, 0x4321);            // bytes of columns 4j+1 .. 4j+4
     const uint32_t llo = l & 0x00FF00FFu, lhi = (l >> 8) & 0x00FF00FFu;
@@ -185,7 +186,7 @@ edge_line4_kernel(const uint8_t* __restrict__ frames, const long long frameStrid
       load_row(r + 2, A2l, A2h, D2l, D2h);
       const uint32_t hl = edge_hits2(A0l, A2l, D0l, D1l, D2l) & keepLo;
       const uint32_t hh = edge_hits2(A0h, A2h, D0h, D1h, D2h) & keepHi;
-      hitsLo += hl; hitsHi += hh;
+      hitsLo += live ? hl : 0u; hitsHi += live ? hh : 0u;
       if (WRAP)
       {
         const uint32_t c0 = 4u * (uint32_t)j;
@@ -254,7 +255,7 @@ cudaError_t launch_edge_line(const uint8_t* frames, long long frameStride, int l
   if (g_edgeVariant == 0 && aligned4 && height < 65536)
   {
     const int words = (width >> 2) - 7;                     // words 4 .. (W-16)/4
-    const int wpr = ((words + 31) / 32) * 32;
+    const int wpr = ((words + 29) / 30) * 32;               // 30 counted words per warp + two halo lanes
     int groups = 512 / wpr;
     if (groups < 1) groups = 1;
     if (groups > (height - 2 + 7) / 8) groups = (height - 2 + 7) / 8;      // at least 8 output rows per band
