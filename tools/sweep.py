@@ -34,6 +34,7 @@ def main():
     sensors.lib().trikb200_setMxnTableMode(int(os.environ.get("OMTAB", "0")))   # -1: arithmetic mxn kernel only
     sensors.lib().trikb200_setMxnTableThreads(int(os.environ.get("OMTHREADS", "0")))
     sensors.lib().trikb200_setLutSkew(int(os.environ.get("SKEW", "1")))
+    sensors.lib().trikb200_setOverlapLaunch(int(os.environ.get("OVERLAP", "1")))   # 0: no programmatic dependent launches
     peak = 6541.1
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
