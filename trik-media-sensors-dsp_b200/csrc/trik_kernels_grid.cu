@@ -481,13 +481,29 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
   // one group ahead arrives after ~500 cycles while an empty group takes ~100.  So whole bitmap rows are staged
   // OO_RING_AHEAD rows ahead into a small ring in shared memory with cp.async, one commit group per row.
   uint16_t* const ring = reinterpret_cast<uint16_t*>(s_raw + ringOfs);
+  // Most rows of most frames are empty, and with ~28 walks resident per SM their cost is instruction issue (measured per
+  // frame: an empty 320x240 frame took 66 k cycles, 121 instructions per row): so the row overhead is kept short -- up to
+  // 256 metapixels per row (W <= 1024) one 16-byte copy per lane fetches a row, one 16-byte load per lane tells whether
+  // it has any set bit at all, and a label row that is known to be zero is not zeroed again.
+  const int chunks = bw >> 3;                                                // 16-byte pieces of a bitmap row (W % 32 == 0)
+  const bool narrow = chunks <= 32;
   auto issue_row = [&](int r)
   {
     if (r < bh)
-      for (int c = lane; c < (bw >> 3); c += 32)
-        cp_async16(ring + (size_t)(r & (OO_RING_ROWS - 1)) * bw + c * 8, bm + (size_t)r * bw + c * 8);
+    {
+      if (narrow)
+      {
+        if (lane < chunks)
+          cp_async16(ring + (r & (OO_RING_ROWS - 1)) * bw + lane * 8, bm + (size_t)r * bw + lane * 8);
+      }
+      else
+        for (int c = lane; c < chunks; c += 32)
+          cp_async16(ring + (size_t)(r & (OO_RING_ROWS - 1)) * bw + c * 8, bm + (size_t)r * bw + c * 8);
+    }
     cp_async_commit();                                                       // also when empty: the group count stays uniform
   };
+  bool zeroPrev = true, zeroCur = true;                                      // the label rows start zeroed
+  const bool vecRows = narrow && ((uint32_t)__cvta_generic_to_shared(rows) & 15u) == 0u;   // (behind the tables they may not be aligned)
   for (int r = 0; r < OO_RING_AHEAD; ++r)
     issue_row(r);
   for (int row = 0; row < bh; ++row)
@@ -499,14 +515,38 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
     {
       // a row without a single detected cell (most rows of most frames): its labels are all 0, nothing else happens
       bool anyOn = false;
-      for (int c = lane; c < bw; c += 32)
-        anyOn |= __popc((unsigned)bmRow[c]) > 2;
-      if (!__any_sync(FULL, anyOn))
+      if (narrow)
       {
+        uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < chunks)
+          wv = *reinterpret_cast<const uint4*>(bmRow + lane * 8);
+        anyOn = (wv.x | wv.y | wv.z | wv.w) != 0u;                           // any bit at all: cheap and conservative
+      }
+      bool some = __any_sync(FULL, anyOn);
+      if (some || !narrow)
+      {
+        anyOn = false;
+#pragma unroll 1
         for (int c = lane; c < bw; c += 32)
-          cur[c] = 0;
-        __syncwarp();
+          anyOn |= __popc((unsigned)bmRow[c]) > 2;
+        some = __any_sync(FULL, anyOn);
+      }
+      if (!some)
+      {
+        if (!zeroCur)
+        {
+          if (vecRows)
+          {
+            if (lane < chunks)
+              *reinterpret_cast<uint4*>(cur + lane * 8) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          else
+            for (int c = lane; c < bw; c += 32)
+              cur[c] = 0;
+          __syncwarp();
+        }
         uint16_t* tmp = prev; prev = cur; cur = tmp;
+        zeroCur = zeroPrev; zeroPrev = true;
         continue;
       }
     }
@@ -622,6 +662,7 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
       __syncwarp();
     }
     uint16_t* tmp = prev; prev = cur; cur = tmp;
+    zeroCur = zeroPrev; zeroPrev = false;                                    // the row just written has labels in it
   }
   // The tail (merge in label order, std::sort, eight targets) is one lane's sequential work on the label tables.  In
   // global memory every step of it is an L2 round trip; frames with few labels (the usual case) first bring their
