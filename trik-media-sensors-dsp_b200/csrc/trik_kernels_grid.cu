@@ -522,15 +522,14 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
           wv = *reinterpret_cast<const uint4*>(bmRow + lane * 8);
         anyOn = (wv.x | wv.y | wv.z | wv.w) != 0u;                           // any bit at all: cheap and conservative
       }
-      bool some = __any_sync(FULL, anyOn);
-      if (some || !narrow)
+      else
       {
-        anyOn = false;
 #pragma unroll 1
         for (int c = lane; c < bw; c += 32)
           anyOn |= __popc((unsigned)bmRow[c]) > 2;
-        some = __any_sync(FULL, anyOn);
       }
+      // (narrow: a row with set bits but no cell above the threshold goes through the group loop, which skips its groups)
+      const bool some = __any_sync(FULL, anyOn);
       if (!some)
       {
         if (!zeroCur)
@@ -595,17 +594,29 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
       __syncwarp();                                                          // the zeroed records before anybody adds to them
       if (lane == 0 && on && carry != 0u)                                    // the run continues from the previous group
         x = (x == 0u || carry < x) ? carry : x;
-      // segmented inclusive scan of "min over non-zero" along the runs
+      // segmented inclusive scan of "min over non-zero" along the runs.  Usually nothing smaller than the label a run
+      // starts with comes in from above further along the run, and then every cell of the run simply takes that label:
+      // one shuffle from the run's first lane and a vote instead of the five scan steps.
       bool flag = !on || !leftOn || lane == 0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
       {
-        const uint32_t y = __shfl_up_sync(FULL, x, d);
-        const bool g2 = __shfl_up_sync(FULL, (int)flag, d) != 0;
-        if (lane >= d && !flag)
+        const unsigned starts = __ballot_sync(FULL, flag) & ((2u << lane) - 1u);   // segment starts at or below this lane (bit 0 always)
+        const uint32_t xs = __shfl_sync(FULL, x, 31 - __clz((int)starts));
+        const bool plain = !on || x == 0u || (xs != 0u && x >= xs);
+        if (__all_sync(FULL, plain))
+          x = on ? xs : 0u;
+        else
         {
-          if (y != 0u && (x == 0u || y < x)) x = y;
-          flag = g2;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+          {
+            const uint32_t y = __shfl_up_sync(FULL, x, d);
+            const bool g2 = __shfl_up_sync(FULL, (int)flag, d) != 0;
+            if (lane >= d && !flag)
+            {
+              if (y != 0u && (x == 0u || y < x)) x = y;
+              flag = g2;
+            }
+          }
         }
       }
       const uint32_t v = on ? x : 0u;
@@ -704,8 +715,11 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
   for (int i = 0; i < 20; ++i) di.v[i] = 0;
   for (int i = 0; i < 8; ++i)                             // cv_ball_detector_seqpass.hpp:572-590
   {
-    // slots past the last label: the reference reads beyond its vector (undefined); defined here as empty
-    const OoCluster c = (i < ncl) ? cl[i] : OoCluster{0, 0, 0};
+    // slots past the last label: the reference reads beyond its vector (undefined); defined here as empty, and an
+    // empty slot (size 0 -> radius 0) never is a target: nothing to compute for it
+    if (i >= ncl)
+      break;
+    const OoCluster c = cl[i];
     int size = (int)sqrtf((float)(uint16_t)c.size);
     const uint32_t radius = (uint32_t)ceilf((float)size / 3.1415927f);
     size = (int)((uint32_t)(radius * 100u * 4u) / (uint32_t)(bw + bh));
