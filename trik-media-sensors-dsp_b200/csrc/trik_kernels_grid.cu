@@ -572,9 +572,8 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
         continue;
       }
       const bool leftOn = lane == 0 ? (carry != 0u) : ((onMask >> (lane - 1)) & 1u);
-      uint32_t mu = p0;                                                      // smallest non-zero up label
-      if (p1 && (p1 < mu || mu == 0)) mu = p1;
-      if (p2 && (p2 < mu || mu == 0)) mu = p2;
+      // smallest non-zero up label: 0 - 1 wraps to the largest value, so it is a plain three-way minimum
+      const uint32_t mu = min(min(p0 - 1u, p1 - 1u), p2 - 1u) + 1u;
       // a run start without any labelled neighbour opens a new label, numbered in raster order
       const bool opens = on && !leftOn && mu == 0u;
       const unsigned openMask = __ballot_sync(FULL, opens);
@@ -598,11 +597,14 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
       // starts with comes in from above further along the run, and then every cell of the run simply takes that label:
       // one shuffle from the run's first lane and a vote instead of the five scan steps.
       bool flag = !on || !leftOn || lane == 0;
+      const unsigned startsAll = __ballot_sync(FULL, flag);
+      bool plainRuns;
       {
-        const unsigned starts = __ballot_sync(FULL, flag) & ((2u << lane) - 1u);   // segment starts at or below this lane (bit 0 always)
+        const unsigned starts = startsAll & ((2u << lane) - 1u);                // segment starts at or below this lane (bit 0 always)
         const uint32_t xs = __shfl_sync(FULL, x, 31 - __clz((int)starts));
         const bool plain = !on || x == 0u || (xs != 0u && x >= xs);
-        if (__all_sync(FULL, plain))
+        plainRuns = __all_sync(FULL, plain);
+        if (plainRuns)
           x = on ? xs : 0u;
         else
         {
@@ -629,6 +631,31 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
       // masses: every on cell except the openers adds (col, row, 1) to its label.  The cells of one label find each
       // other with one MATCH; the lowest lane of each group adds for all of them (sum of their columns from the bit
       // positions of the peer mask), all labels of the group at once.
+      if (plainRuns)
+      {
+        // every run carries one label: its first lane adds for the whole run (lanes first..e1-1; an opener does not count
+        // itself).  Two runs of a group may carry the same label: reductions / atomics.
+        if (flag && on)
+        {
+          const unsigned above = startsAll & ~((2u << lane) - 1u);               // segment starts above this lane
+          const int e1 = above ? __ffs((int)above) - 1 : 32;
+          const int first = lane + (opens ? 1 : 0);
+          const int cnt = e1 - first;
+          if (cnt > 0 && v != 0u)
+          {
+            const int sumc = base * cnt + ((first + e1 - 1) * cnt) / 2;
+            if (tablesInSmem)
+            {
+              atomicAdd(&cl[v].x, sumc); atomicAdd(&cl[v].y, row * cnt); atomicAdd(&cl[v].size, cnt);
+            }
+            else
+            {
+              red_add_global(&cl[v].x, sumc); red_add_global(&cl[v].y, row * cnt); red_add_global(&cl[v].size, cnt);
+            }
+          }
+        }
+      }
+      else
       {
         const bool needAdd = on && !opens && v != 0u;
         const unsigned peers = __match_any_sync(FULL, needAdd ? v : 0xFFFFFFFFu);
