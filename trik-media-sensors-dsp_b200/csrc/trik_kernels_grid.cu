@@ -719,19 +719,68 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
     cl = sc;
     eq = se;
   }
+  ncl = __shfl_sync(FULL, ncl, 0);
+  const bool tablesNear = tablesInSmem || ncl <= tailCap;  // the tables the tail works on are in shared memory
+  if (lane == 0)
+    for (int i = 0; i < ncl; ++i)                         // postProcessing (:115-124)
+    {
+      const int e = eq[i];
+      if (i != e)
+      {
+        cl[e].x += cl[i].x; cl[e].y += cl[i].y; cl[e].size += cl[i].size;
+        cl[i].size = 0;
+      }
+    }
+  __syncwarp();
+  // std::sort(..., compareTargetBySize) (:126), of which only the first eight records are ever read (:572-590).  The
+  // order std::sort leaves EQUAL sizes in is observable, so it is restated exactly (oo_std_sort) -- but one lane sorting
+  // 66 records takes 35 k cycles.  When the sizes decide by themselves, any correct sort gives the same first eight: the
+  // warp selects the maximum eight times, and only if two non-empty clusters tie for one of those places (or the tables
+  // are large) the sequential sort runs.  Records of size 0 never become targets, so ties among them do not matter.
+  int sel[8];
+  int nsel = 0;
+  bool bySelection = tablesNear && ncl >= 32 && ncl <= 256;   // (a short table is sorted faster than it is searched eight times)
+  if (bySelection)
+  {
+    uint32_t taken = 0u;                                  // bit j: record lane + 32 j
+    bool done = false, tie = false;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+    {
+      sel[r] = 0;
+      if (!done)
+      {
+        int best = -1, bestJ = 0, nBest = 0;
+        for (int j = 0; lane + 32 * j < ncl; ++j)
+          if (!((taken >> j) & 1u))
+          {
+            const int sz = cl[lane + 32 * j].size;
+            if (sz > best) { best = sz; bestJ = j; nBest = 1; }
+            else if (sz == best) ++nBest;
+          }
+        const int m = __reduce_max_sync(FULL, best);
+        if (m <= 0)
+          done = true;                                    // only empty clusters left
+        else if (__reduce_add_sync(FULL, best == m ? nBest : 0) > 1)
+        {
+          done = true; tie = true;                        // two clusters of this size: std::sort's own order decides
+        }
+        else
+        {
+          const int owner = __ffs((int)__ballot_sync(FULL, best == m)) - 1;
+          sel[r] = __shfl_sync(FULL, lane + 32 * bestJ, owner);
+          if (lane == owner) taken |= 1u << bestJ;
+          nsel = r + 1;
+        }
+      }
+    }
+    bySelection = !tie;
+  }
   if (lane != 0)
     return;
-
-  for (int i = 0; i < ncl; ++i)                           // postProcessing (:115-124)
-  {
-    const int e = eq[i];
-    if (i != e)
-    {
-      cl[e].x += cl[i].x; cl[e].y += cl[i].y; cl[e].size += cl[i].size;
-      cl[i].size = 0;
-    }
-  }
-  oo_std_sort(cl, ncl);                                   // std::sort(..., compareTargetBySize) (:126)
+  if (!bySelection)
+    oo_std_sort(cl, ncl);
+  const int nTargets = bySelection ? nsel : (ncl < 8 ? ncl : 8);
 
   ObjOut r;
   for (int i = 0; i < 24; ++i) r.t[i] = 0;
@@ -740,13 +789,14 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
   const int W = g.width, H = g.height;
   DrawInfo di;
   for (int i = 0; i < 20; ++i) di.v[i] = 0;
+#pragma unroll
   for (int i = 0; i < 8; ++i)                             // cv_ball_detector_seqpass.hpp:572-590
   {
     // slots past the last label: the reference reads beyond its vector (undefined); defined here as empty, and an
     // empty slot (size 0 -> radius 0) never is a target: nothing to compute for it
-    if (i >= ncl)
+    if (i >= nTargets)
       break;
-    const OoCluster c = cl[i];
+    const OoCluster c = cl[bySelection ? sel[i] : i];
     int size = (int)sqrtf((float)(uint16_t)c.size);
     const uint32_t radius = (uint32_t)ceilf((float)size / 3.1415927f);
     size = (int)((uint32_t)(radius * 100u * 4u) / (uint32_t)(bw + bh));
