@@ -181,6 +181,9 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    # the workers are forked pool children; one call in this (parent) process as well, so that the host-built reference
+    # (oracle/_ref/libtrikref_wl.so) is visibly the code this arm runs
+    _cpu_worker((KIND, [0, 1], 1))
     per_core = 96
     vals = []
     for _ in range(args.warmup):
@@ -207,6 +210,205 @@ def run_reference_arm(args, rank):
 
 
 # ---------------------------------------------------------------------------------------------
+# beside the headline: the rest of BASELINE.json's metric ("320x240 & 640x480", configs 3 and 4)
+# ---------------------------------------------------------------------------------------------
+SIZES = ((320, 240, 4096), (640, 480, 1024))          # (W, H, frames per launch): 629 MB per batch, larger than L2
+MIX_KINDS = ["wo", "wl", "ol", "oo", "om"]
+
+
+def _in_alg(xdm, kind, grid=(3, 3)):
+    if kind == "oo":
+        return xdm.ObjInArgsAlg(1, 0, 20, 80, 20, 50, 30, 0)
+    if kind == "om":
+        return xdm.MxnInArgsAlg(grid[0], grid[1])
+    return xdm.RangeInArgsAlg(*IN_ARGS)
+
+
+def extras(line, args, torch, dev, stream, sptr, timed, peak, sampler_factory):
+    """All five sensors at both sizes (frames resident), preview-on throughput, config 3 (mxn 3x3 / 5x5 on 640x480), and
+    the host-buffer (e2e) figure of the object and mxn sensors.  CUDA events on the launching stream, 3 warm-up + 10
+    timed steps each, inputs (629 MB) larger than L2; explanatory only -- `value` is the BASELINE headline."""
+    from trik_media_sensors_dsp_b200 import open_sensor, synth, xdm, sensors as _sensors
+    uniq = 64
+    sampler = sampler_factory()
+    sampler.start()
+    t_start = time.time()
+    for (w, h, n) in SIZES:
+        tag = "other_sensors" if (w, h) == (W, H) else "other_sensors_%dx%d" % (w, h)
+        out = {}
+        previews = {}
+        e2e = {}
+        fb = w * h * 2
+        host = torch.empty((n, fb), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        d_frames = torch.empty((n, fb), dtype=torch.uint8, device=dev)
+        cases = [("wl", "scene", None), ("ol", "scene", None), ("wo", "scene", None), ("oo", "scene", None), ("om", "grid", (3, 3))]
+        if (w, h) == (640, 480):
+            cases.append(("om", "grid", (5, 5)))            # BASELINE config 3: mxn 3x3 and 5x5, 1024 x 640x480
+        for kind, fam, grid in cases:
+            if (w, h) == (W, H) and kind == KIND:
+                continue                                    # the headline itself
+            k = xdm.KIND_OF[kind]
+            layout = _sensors.layout_of(k)
+            kw = {"m": grid[0], "n": grid[1]} if grid else {}
+            hu = synth.make_batch(fam, range(uniq), w, h, layout, **kw)
+            for i in range(0, n, uniq):
+                hv[i:i + uniq] = hu[:min(uniq, n - i)]
+            d_frames.copy_(host)
+            orec = C.sizeof(xdm.OUT_ARGS_ALG[k])
+            o_out = torch.zeros((n, orec), dtype=torch.uint8, device=dev)
+            oc = open_sensor(kind, w, h)
+            oia = _in_alg(xdm, kind, grid or (3, 3))
+
+            def step():
+                r, _ = oc.process_batch(d_frames.data_ptr(), oia, frames_device=True, frame_stride=fb, num_frames=n,
+                                        out_device_ptr=o_out.data_ptr(), stream=sptr, flags=xdm.BATCH_ASYNC)
+                assert r == 0, _sensors.last_error()
+
+            for _ in range(3):
+                step()
+            ms = timed(step, 10) / 10
+            name = kind if not grid or grid == (3, 3) else "%s_%dx%d" % (kind, grid[0], grid[1])
+            out[name] = {"frames_per_sec": n / (ms / 1000.0), "ms_per_step": ms, "hbm_frac": n * fb / (ms / 1000.0) / 1e9 / peak,
+                         "frames": fam, "batch": n}
+            if kind in ("wl", "oo"):
+                # the RGB565X preview with overlays, written to device memory at 1:1: 2 B/px read + 2 B/px written
+                pv = torch.empty((n, fb), dtype=torch.uint8, device=dev)
+
+                def pstep():
+                    r, _ = oc.process_batch(d_frames.data_ptr(), oia, frames_device=True, frame_stride=fb, num_frames=n,
+                                            out_device_ptr=o_out.data_ptr(), stream=sptr, flags=xdm.BATCH_ASYNC,
+                                            previews_device_ptr=pv.data_ptr(), preview_stride=fb)
+                    assert r == 0, _sensors.last_error()
+
+                for _ in range(3):
+                    pstep()
+                pms = timed(pstep, 10) / 10
+                previews[kind] = {"frames_per_sec": n / (pms / 1000.0), "ms_per_step": pms,
+                                  "hbm_frac_4B_per_px": n * 2 * fb / (pms / 1000.0) / 1e9 / peak}
+                del pv
+            if kind in ("oo", "om"):
+                # host buffers through trikb200_processBatch: pinned frames H2D + kernels + records D2H inside the timed region
+                outs = (xdm.OUT_ARGS_ALG[k] * n)()
+
+                def hstep():
+                    r, _ = oc.process_batch(hv, oia, out_algs=outs, stream=sptr)
+                    assert r == 0, _sensors.last_error()
+
+                hstep()
+                hms = timed(hstep, 3) / 3
+                e2e[name] = {"frames_per_sec": n / (hms / 1000.0), "ms_per_step": hms, "h2d_bytes_per_step": n * fb,
+                             "d2h_bytes_per_step": n * orec}
+            oc.close()
+            del o_out
+        line[tag] = out
+        line["preview_on" if (w, h) == (W, H) else "preview_on_%dx%d" % (w, h)] = previews
+        line["e2e_other" if (w, h) == (W, H) else "e2e_other_%dx%d" % (w, h)] = e2e
+        del d_frames, host
+    line["config3_mxn"] = {"workload": "mxn grid colour sensor, 1024 x 640x480 YUV422P grid frames, frames resident",
+                           "3x3": line["other_sensors_640x480"]["om"], "5x5": line["other_sensors_640x480"]["om_5x5"],
+                           "e2e_3x3": line["e2e_other_640x480"].get("om"), "e2e_5x5": line["e2e_other_640x480"].get("om_5x5")}
+    line["extras_clocks"] = sampler.stop()
+    line["extras_wall_s"] = time.time() - t_start
+
+
+def config4_mixed(args, torch, dist, dev, rank, world):
+    """BASELINE config 4: mixed line + object + mxn instances over `--mixed-streams` concurrent streams, ONE codec handle per
+    stream (the reference's model: one instance per sensor), streams round-robin over the ranks, every time step one frame
+    of every stream through trikb200_processMixed with PINNED host frames; at the end the records of all ranks are gathered
+    (the only exchange).  Total work is fixed as N grows (strong scaling).  Timed on the host (the call is synchronous and
+    spans many CUDA streams), synchronise + barrier on both sides, max over ranks."""
+    from trik_media_sensors_dsp_b200 import open_sensor, synth, xdm, sensors as _sensors, sharding, launch_count
+    streams, T = args.mixed_streams, args.mixed_steps
+    mine = sharding.streams_of_rank(streams, world, rank)
+    pool_n = 16
+    fb = W * H * 2
+    # pinned pool of frames: 16 distinct per kind
+    pool = torch.empty((len(MIX_KINDS), pool_n, fb), dtype=torch.uint8, pin_memory=True)
+    pv = pool.numpy()
+    for ki, kind in enumerate(MIX_KINDS):
+        fam = "blobs" if kind == "oo" else ("grid" if kind == "om" else "scene")
+        pv[ki] = synth.make_batch(fam, range(pool_n), W, H, _sensors.layout_of(xdm.KIND_OF[kind]))
+    codecs = {s: open_sensor(MIX_KINDS[s % 5], W, H) for s in mine}
+    rec_max = 400
+    results = np.zeros((T, len(mine), rec_max), dtype=np.uint8)
+    in_first = {k: _in_alg(xdm, k) for k in MIX_KINDS}
+    in_later = dict(in_first)
+    in_later["oo"] = xdm.ObjInArgsAlg(0, 0, 0, 0, 0, 0, 0, 0)              # the range is carried state from step 0 on
+    tables = []
+    for t in range(T):
+        entries = (xdm.MixedEntry * len(mine))()
+        for j, s in enumerate(mine):
+            kind = MIX_KINDS[s % 5]
+            e = entries[j]
+            e.handle = codecs[s].handle
+            e.frame = pv[s % 5, (s + t) % pool_n].ctypes.data
+            e.inArgsAlg = C.addressof(in_first[kind] if t == 0 else in_later[kind])
+            e.outArgsAlg = results[t, j].ctypes.data
+            e.seed = 7
+        tables.append(entries)
+    L = _sensors.lib()
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def run_all():
+        for t in range(T):
+            r = L.trikb200_processMixed(tables[t], len(mine))
+            assert r == 0, _sensors.last_error()
+        # final result gather: the only exchange between the GPUs
+        if world > 1:
+            local = torch.from_numpy(results.reshape(-1, rec_max)).to(dev)
+            width = (streams + world - 1) // world * T
+            pad = torch.zeros((width, rec_max), dtype=torch.uint8, device=dev)
+            pad[:local.shape[0]] = local
+            outs = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(outs, pad)
+            return outs
+        return None
+
+    run_all()                                                              # warm-up: allocations, tables, module load
+    for c in codecs.values():
+        assert c.set_params(W, H) == 0                                     # restart every stream's carried state
+    sync()
+    l0 = launch_count()
+    t0 = time.perf_counter()
+    run_all()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    launches = launch_count() - l0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    sync()
+    # self-check on a sample: the same frames through sequential process() calls on a fresh handle
+    bad = 0
+    for j, s in list(enumerate(mine))[:10]:
+        kind = MIX_KINDS[s % 5]
+        fresh = open_sensor(kind, W, H)
+        nb = {"om": 36, "oo": 24}.get(kind, 3)
+        for t in range(T):
+            ret, oa = fresh.process(pv[s % 5, (s + t) % pool_n], in_first[kind] if t == 0 else in_later[kind], seed=7)
+            if ret != 0 or bytes(results[t, j, :nb]) != bytes(memoryview(oa.alg))[:nb]:
+                bad += 1
+        fresh.close()
+    for c in codecs.values():
+        c.close()
+    total = streams * T
+    h2d = total * fb
+    return {"workload": "mixed WO/WL/OL/OO/OM instances, %d streams (one codec handle each) x %d frames of %dx%d, streams "
+                        "round-robin over %d GPU(s), pinned host frames through trikb200_processMixed, final gather of the records"
+                        % (streams, T, W, H, world),
+            "frames_per_sec": total / dt, "wall_s": dt, "scaling": "strong", "n_gpus": world,
+            "gpu_launches_rank0": int(launches), "launches_per_time_step_rank0": launches / float(T),
+            "h2d_bytes_total": h2d, "h2d_gbs": h2d / dt / 1e9, "mismatches_vs_sequential_process_rank0_sample": bad,
+            "timing": "host wall clock around the synchronous calls, device synchronised on both sides, max over ranks"}
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def main():
@@ -219,7 +421,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sustained", action="store_true", help="skip the 1.5 s steady-state phase")
     ap.add_argument("--no-repeats", action="store_true", help="time the K steps once only")
-    ap.add_argument("--no-others", action="store_true", help="skip the short resident measurement of the other four sensors")
+    ap.add_argument("--no-others", action="store_true", help="skip the other sensors / sizes / configs measured beside the headline")
+    ap.add_argument("--no-mixed", action="store_true", help="skip BASELINE config 4 (mixed sensor instances over 1024 streams)")
+    ap.add_argument("--mixed-streams", type=int, default=1024)
+    ap.add_argument("--mixed-steps", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -352,6 +557,10 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, e2e_steps)
 
+    mixed = None
+    if not args.no_mixed:
+        mixed = config4_mixed(args, torch, dist, dev, rank, world)
+
     ms_per_step = ms_total / args.steps
     value = world * n / (ms_per_step / 1000.0)
     e2e_value = world * n / (ms_e2e / e2e_steps / 1000.0)
@@ -378,42 +587,12 @@ def main():
             "clocks": clocks,
             "repeat_ms_per_step": [r / args.steps for r in runs],
             "sustained": sustained,
+            "config4_mixed_streams": mixed,
         }
         line["config"]["host_affinity"] = ("rank bound to its GPU's NUMA node: %d of %d CPUs" % (len(bound[1]), len(bound[0]))
                                            if bound else "unbound (NVML affinity query unavailable)")
         if not args.no_others and world == 1:
-            # beside the headline: the other four sensors on the same batch shape, frames resident, 10 steps each
-            # (explanatory only -- `value` above is the BASELINE metric)
-            others = {}
-            from trik_media_sensors_dsp_b200 import sensors as _sensors
-            for kind in ("ol", "wo", "om", "oo"):
-                layout = _sensors.layout_of(xdm.KIND_OF[kind])
-                fam = "grid" if kind == "om" else "scene"
-                hu = synth.make_batch(fam, range(uniq), W, H, layout)
-                hv[:] = 0
-                for i in range(0, n, uniq):
-                    hv[i:i + uniq] = hu[:min(uniq, n - i)]
-                d_frames.copy_(host)
-                k = xdm.KIND_OF[kind]
-                orec = C.sizeof(xdm.OUT_ARGS_ALG[k])
-                o_out = torch.zeros((n, orec), dtype=torch.uint8, device=dev)
-                oc = open_sensor(kind, W, H)
-                oia = (xdm.ObjInArgsAlg(1, 0, 20, 80, 20, 50, 30, 0) if kind == "oo"
-                       else (xdm.MxnInArgsAlg(3, 3) if kind == "om" else xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 40, 0)))
-
-                def other_step():
-                    r, _ = oc.process_batch(d_frames.data_ptr(), oia, frames_device=True, frame_stride=fbytes, num_frames=n,
-                                            out_device_ptr=o_out.data_ptr(), stream=sptr, flags=xdm.BATCH_ASYNC)
-                    assert r == 0
-
-                for _ in range(3):
-                    other_step()
-                oms = timed(other_step, 10) / 10
-                others[kind] = {"frames_per_sec": n / (oms / 1000.0), "ms_per_step": oms,
-                                "hbm_frac": n * W * H * 2 / (oms / 1000.0) / 1e9 / peak, "frames": fam}
-                oc.close()
-                del o_out
-            line["other_sensors"] = others
+            extras(line, args, torch, dev, stream, sptr, timed, peak, sampler_factory=lambda: ClockSampler(local_rank))
         if not args.no_cpu and world == 1:
             if bound:
                 os.sched_setaffinity(0, bound[0])          # the CPU baseline uses every core of the box again

@@ -6,7 +6,7 @@
  *     argv[2]  this repository's drop-in alias library  (libtrik_vidtranscode_cv_<kind>.so)
  * Both export the reference's symbol TRIK_VIDTRANSCODE_CV_FXNS.  The SAME compiled driver code and the
  * SAME struct definitions (include/trik_b200.h) are used for both; OutArgs and the preview image must
- * come out byte for byte identical.  argv[3] = kind (wo|wl|ol|om).  Exit code 0 = identical.
+ * come out byte for byte identical.  argv[3] = kind (wo|wl|ol|om|oo).  Exit code 0 = identical.
  */
 #include <dlfcn.h>
 #include <stdint.h>
@@ -53,10 +53,32 @@ static void make_frame(unsigned char* f, int planar, int variant)
     }
 }
 
+/* object sensor: a dark YUV422P frame with 14 saturated red blocks of different sizes (>= 8 labels: with fewer the
+ * reference reads past its cluster vector, ov7670/object_sensor/include/internal/cv_ball_detector_seqpass.hpp:575-589),
+ * two of them of equal size so that the order std::sort leaves equal sizes in shows */
+static void make_object_frame(unsigned char* f, int variant)
+{
+  int k, r, c;
+  memset(f, 24, (size_t)W * H);
+  memset(f + (size_t)W * H, 128, (size_t)W * H);
+  for (k = 0; k < 14; ++k)
+  {
+    const int bh = 4 * (1 + (k == 13 ? 5 : k) % 7), bw = 4 * (1 + (k == 13 ? 5 : k) % 9);
+    const int r0 = 4 * ((7 * k + 3 * variant) % ((H - 40) / 4)), c0 = 4 * ((11 * k * k + 5 * variant + 2 * k) % ((W - 48) / 4));
+    for (r = r0; r < r0 + bh; ++r)
+      for (c = c0; c < c0 + bw; c += 2)
+      {
+        f[(size_t)r * W + c] = 120; f[(size_t)r * W + c + 1] = 120;
+        f[(size_t)(H + r) * W + c] = 240; f[(size_t)(H + r) * W + c + 1] = 90;
+      }
+  }
+}
+
 static int run(IVIDTRANSCODE_Fxns* fx, const char* kind, int nframes, Result* out)
 {
   const int planar = strcmp(kind, "wo") != 0 && strcmp(kind, "wl") != 0;
   const int isMxn = strcmp(kind, "om") == 0;
+  const int isObj = strcmp(kind, "oo") == 0;
   TRIK_VIDTRANSCODE_CV_Params params;
   TRIK_VIDTRANSCODE_CV_DynamicParams dyn;
   IVIDTRANSCODE_Status status;
@@ -111,10 +133,13 @@ static int run(IVIDTRANSCODE_Fxns* fx, const char* kind, int nframes, Result* ou
     XDM_BufDesc outBufs;
     XDAS_Int8* outPtr[1];
     XDAS_Int32 outSize[1];
-    union { TRIKB200_RangeInArgs r; TRIKB200_MxnInArgs m; } in;
-    union { TRIKB200_TargetOutArgs t; TRIKB200_MxnOutArgs m; } oa;
+    union { TRIKB200_RangeInArgs r; TRIKB200_MxnInArgs m; TRIKB200_ObjInArgs o; } in;
+    union { TRIKB200_TargetOutArgs t; TRIKB200_MxnOutArgs m; TRIKB200_ObjOutArgs o; } oa;
     Result* res = &out[f];
-    make_frame(frame, planar, f);
+    if (isObj)
+      make_object_frame(frame, f);
+    else
+      make_frame(frame, planar, f);
     res->preview = (unsigned char*)malloc((size_t)(W / 2) * (H / 2) * 2);
     memset(res->preview, 0x5A, (size_t)(W / 2) * (H / 2) * 2);
     memset(&inBufs, 0, sizeof(inBufs));
@@ -130,6 +155,16 @@ static int run(IVIDTRANSCODE_Fxns* fx, const char* kind, int nframes, Result* ou
       oa.m.base.size = sizeof(oa.m);
       res->ret = fx->process((IVIDTRANSCODE_Handle)h, &inBufs, &outBufs, &in.m.base, &oa.m.base);
       res->algSize = 12 * 4; memcpy(res->alg, &oa.m.alg, 48); res->base = oa.m.base;
+    }
+    else if (isObj)
+    {
+      in.o.base.size = sizeof(in.o); in.o.base.numBytes = W * H * 2; in.o.base.inputID = f + 1;
+      in.o.alg.setHsvRange = (f == 0 || f == 2);       /* frames 1 and 3 run on the range the handle carries */
+      in.o.alg.detectHue = (f == 2) ? 350 : 0; in.o.alg.detectHueTol = 40;      /* 350 +- 40 wraps around 0 */
+      in.o.alg.detectSat = 60; in.o.alg.detectSatTol = 40; in.o.alg.detectVal = 60; in.o.alg.detectValTol = 40;
+      oa.o.base.size = sizeof(oa.o);
+      res->ret = fx->process((IVIDTRANSCODE_Handle)h, &inBufs, &outBufs, &in.o.base, &oa.o.base);
+      res->algSize = 24; memcpy(res->alg, oa.o.alg.target, 24); res->base = oa.o.base;
     }
     else
     {
@@ -155,7 +190,7 @@ int main(int argc, char** argv)
   void *la, *lb;
   IVIDTRANSCODE_Fxns *fa, *fb;
   int f, rc, bad = 0;
-  if (argc < 4) { fprintf(stderr, "usage: %s <reference.so> <dropin.so> <wo|wl|ol|om>\n", argv[0]); return 2; }
+  if (argc < 4) { fprintf(stderr, "usage: %s <reference.so> <dropin.so> <wo|wl|ol|om|oo>\n", argv[0]); return 2; }
   la = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
   lb = dlopen(argv[2], RTLD_NOW | RTLD_LOCAL);
   if (!la || !lb) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 3; }

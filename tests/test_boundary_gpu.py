@@ -198,3 +198,38 @@ def test_preview_size_is_reported():
     assert ret == 0 and not big[160 * 120 * 2:].any() and big[:160 * 120 * 2].any()
     assert oa.base.encodedBuf[0].bufSize == 120 * 160 * 2 and oa.base.bitsGenerated[0] == 120 * 160 * 2 * 8
     c.close()
+
+
+@pytest.mark.parametrize("kind", xdm.KIND_NAMES)
+def test_line_length_is_validated(kind):
+    """Documented deviation (DESIGN.md "Boundary"): the kernels read rows with 16-byte loads, so control(XDM_SETPARAMS)
+    refuses an inputLineLength that is not a multiple of 16 or does not cover a row -- as IALG_EFAIL, never as a CUDA
+    fault -- and the handle stays usable afterwards."""
+    w, h = 320, 240
+    c = open_sensor(kind, w, h)
+    row = w if sensors.layout_of(xdm.KIND_OF[kind]) == "yuv422p" else 2 * w
+    assert c.set_params(w, h, line_length=row + 8) == xdm.IALG_EFAIL      # misaligned rows
+    assert c.set_params(w, h, line_length=0) == xdm.IALG_EFAIL            # explicit size, no stride
+    assert c.set_params(w, h, line_length=row - 16) == xdm.IALG_EFAIL     # stride shorter than a row
+    ret, _ = c.process(frame_for(kind), default_in_alg(kind))             # no valid geometry: EFAIL, no crash
+    assert ret == xdm.XDM_EFAIL
+    assert c.set_params(w, h, line_length=row + 16) == 0                  # padded rows are fine
+    assert c.set_params(w, h) == 0
+    ret, _ = c.process(frame_for(kind), default_in_alg(kind))
+    assert ret == 0
+    c.close()
+
+
+def test_mxn_grid_arguments_are_validated_as_int32():
+    """widthM / heightN are XDAS_Int32: 257 must not be taken for 1 (nor 256 for 0); non-positive values and
+    products above 100 (outColor[100]) are refused."""
+    w, h = 320, 240
+    c = open_sensor("om", w, h)
+    fr = frame_for("om")
+    for m, n in ((257, 1), (1, 258), (256, 1), (0, 3), (3, 0), (-1, 3), (11, 10), (101, 1)):
+        ret, _ = c.process(fr, xdm.MxnInArgsAlg(m, n))
+        assert ret == xdm.XDM_EFAIL, (m, n)
+    for m, n in ((1, 1), (10, 10), (100, 1), (1, 100)):
+        ret, _ = c.process(fr, xdm.MxnInArgsAlg(m, n))
+        assert ret == 0, (m, n)
+    c.close()

@@ -21,7 +21,7 @@ def checker(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("kind", ["wl", "wo", "ol", "om"])
+@pytest.mark.parametrize("kind", ["wl", "wo", "ol", "om", "oo"])
 def test_c_caller_gets_identical_results(checker, kind):
     res = subprocess.run([checker, os.path.join(oracle.REF_DIR, "libtrikref_%s.so" % kind), build.alias_path(kind), kind],
                          capture_output=True, text=True, timeout=300)

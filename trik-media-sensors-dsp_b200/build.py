@@ -57,12 +57,40 @@ def build(force=False, verbose=False):
         with open(STAMP) as f:
             if f.read().strip() == digest and all(os.path.exists(alias_path(k)) for k in KINDS):
                 return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-I", INCLUDE, "-I", CSRC, "-o", LIB]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    # one object per source, compiled in parallel and only when that source (or a header / flag) changed, then one link
+    objdir = os.path.join(HERE, ".obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr = hashlib.sha256()
+    for name in HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            hdr.update(f.read())
+    for name in ("trik_b200.h", "trik_xdm.h"):
+        with open(os.path.join(INCLUDE, name), "rb") as f:
+            hdr.update(f.read())
+    hdr.update(" ".join(NVCC_FLAGS).encode())
+
+    def compile_one(src):
+        with open(os.path.join(CSRC, src), "rb") as f:
+            key = hashlib.sha256(hdr.digest() + f.read()).hexdigest()
+        obj = os.path.join(objdir, src + ".o")
+        keyfile = obj + ".key"
+        if not force and os.path.exists(obj) and os.path.exists(keyfile):
+            with open(keyfile) as f:
+                if f.read().strip() == key:
+                    return obj
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-I", INCLUDE, "-I", CSRC, "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+        with open(keyfile, "w") as f:
+            f.write(key)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    subprocess.run([_nvcc()] + NVCC_FLAGS + ["-shared", "-o", LIB] + objs, check=True)
     # alias libraries: re-export one sensor's tables under the reference's symbol names
     # (TRIK_VIDTRANSCODE_CV_FXNS / TRIK_VIDTRANSCODE_CV_IALG, <sensor>/trik_vidtranscode_cv.h:17-18)
     for kind in KINDS:

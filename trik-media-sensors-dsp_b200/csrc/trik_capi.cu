@@ -306,6 +306,12 @@ bool instance_setup(Instance* in, int width, int height, int lineLength, int out
   // sizes where they would wrap are outside what it supports and are refused here
   if (in->kind == KIND_OO && (long long)(width / 4) * (height / 4) > 65536LL)
     return false;
+  // The kernels read rows with 16-byte loads at row * lineLength + 16 * chunk: a stride that is not a multiple of 16 or
+  // does not cover a row (2 * W bytes for YUV422, W per plane for YUV422P) cannot be served.  The reference accepts any
+  // value here and fails (or reads out of bounds) later; this is the documented deviation (DESIGN.md "Boundary").
+  if (width > 0 && height > 0
+      && ((lineLength & 15) != 0 || lineLength < (kind_is_planar(in->kind) ? width : 2 * width)))
+    return false;
   in->geo.width = width;
   in->geo.height = height;
   in->geo.lineLength = lineLength;
@@ -422,7 +428,7 @@ void merge_result(int kind, const void* inArgsAlg, const uint8_t* rec, const uin
     case KIND_OM:
     {
       const TRIKB200_MxnInArgsAlg* ia = reinterpret_cast<const TRIKB200_MxnInArgsAlg*>(inArgsAlg);
-      const int cells = (int)(uint8_t)ia->widthM * (int)(uint8_t)ia->heightN;
+      const int cells = ia->widthM * ia->heightN;          // validated by enqueue_batch: 1 <= cells <= 100
       memcpy(dst, rec, sizeof(int32_t) * (size_t)cells);   // only counter entries are assigned (:605-618)
       break;
     }
@@ -506,8 +512,8 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
     if (kind == KIND_OM)
     {
       const TRIKB200_MxnInArgsAlg* a = reinterpret_cast<const TRIKB200_MxnInArgsAlg*>(ia);
-      const int M = (uint8_t)a->widthM, N = (uint8_t)a->heightN;
-      if (M == 0 || N == 0 || M * N > 100)
+      const int M = a->widthM, N = a->heightN;
+      if (M < 1 || N < 1 || M > 100 || N > 100 || M * N > 100)
       {
         // the reference divides by zero / overruns outColor[100] (mxn_sensor/.../cv_ball_detector_seqpass.hpp:587-588,612)
         set_error("mxn sensor: widthM and heightN must be >= 1 with widthM*heightN <= 100");
@@ -666,7 +672,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       break;
     }
     case KIND_OM:
-      if (b.outOnDevice)
+      if (b.outOnDevice || b.async)                       // whole records reach the caller: entries past M*N are 0
         CUDA_TRY(cudaMemsetAsync(dOut, 0, recBytes * b.n, s));
       if (g_mxnTableMode >= 0)
       {
@@ -1311,7 +1317,7 @@ XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Bat
   if (batch->numFrames == 0)
     return IVIDTRANSCODE_EOK;
   const size_t fbytes = in->frame_bytes();
-  if (batch->numFrames > 1 && ((size_t)batch->frameStride < fbytes || (batch->frameStride & 15)))
+  if (batch->numFrames > 1 && (batch->frameStride < (int64_t)fbytes || (batch->frameStride & 15)))
   {
     set_error("frameStride must cover a frame and be a multiple of 16");
     return IVIDTRANSCODE_EFAIL;

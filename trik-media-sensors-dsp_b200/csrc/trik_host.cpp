@@ -134,8 +134,9 @@ void prepare_frame_params(int kind, const Geometry& g, const void* inArgsAlg, Ca
     {
       // ov7670/mxn_sensor/include/internal/cv_ball_detector_seqpass.hpp:585-588 (names swapped there)
       const TRIKB200_MxnInArgsAlg* a = static_cast<const TRIKB200_MxnInArgsAlg*>(inArgsAlg);
-      fp.gridRows = (uint8_t)a->widthM;
-      fp.gridCols = (uint8_t)a->heightN;
+      // callers validate 1 <= widthM, heightN and widthM * heightN <= 100 on the int32 values first (trik_capi.cu)
+      fp.gridRows = (uint32_t)a->widthM;
+      fp.gridCols = (uint32_t)a->heightN;
       break;
     }
     default:

@@ -271,8 +271,10 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
     }
     uint32_t sxPass = passes * ((uint32_t)cc * 8u) + inIdx;
 
-    // group reduction
-    const unsigned am = __activemask();
+    // group reduction.  The row loop's trip count differs between the lanes of a warp when cpr is not a multiple of 32:
+    // reconverge first, and name the lanes by the group layout (whole warps whenever gthreads % 32 == 0, the usual case)
+    __syncwarp();
+    const unsigned am = (gthreads & 31) == 0 ? 0xFFFFFFFFu : __activemask();
     passes = __reduce_add_sync(am, passes);
     sxPass = __reduce_add_sync(am, sxPass);
     syPass = __reduce_add_sync(am, syPass);
