@@ -322,9 +322,11 @@ void trikb200_setOverlapLaunch(XDAS_Int32 on);
 /* tuning knob: webcam object sensor batches whose frames share one threshold set can run through a chroma-indexed
  * detection table (results identical): 0 = automatic (default), 1 = whenever possible, -1 = never */
 void trikb200_setLutMode(XDAS_Int32 mode);
-/* tuning knob: the mxn sensor's per-pixel colour bin (H>>3, S>>6, V>>6) is one fixed function of (Y,U,V); batches can
- * gather it from a 2^24-entry table built once per device and process, at the first mxn call (32 MB; results identical,
- * see DESIGN.md 3.4): 0 or 1 = yes (default; measured faster from a single frame up), -1 = never (arithmetic kernel) */
+/* tuning knob: the mxn sensor's per-pixel colour bin (H>>3, S>>6, V>>6) is one fixed function of (Y,U,V), tabulated once
+ * per device and process at the first mxn call (2^24 entries, 32 MB; results identical):
+ * 0 (default) = majority pass first -- a cell in which one bin provably holds more than half of the pixels is decided
+ * without a histogram -- and the table-gather histogram kernel for the cell rows that leaves undecided;
+ * 1 = the histogram kernel for every cell row; -1 = no table at all (arithmetic kernel) */
 void trikb200_setMxnTableMode(XDAS_Int32 mode);
 /* tuning knob: 1 (default) = the shared-memory detection table of the object sensors is laid out with skewed rows (260
  * instead of 256 bytes apart): no bank conflicts when the chroma of neighbouring pixels differs by a little (camera noise),

@@ -42,7 +42,7 @@ def _check(codec, orc, frames, m, n, tag):
         ok, exp = orc.process(frames[i], oracle.MxnInArgs(m, n))
         assert ok == 1
         want.append(list(exp.outColor[:m * n]))
-    for mode in (1, -1):
+    for mode in (0, 1, -1):            # majority pass + histogram rest (default) / histogram table only / arithmetic
         lib().trikb200_setMxnTableMode(mode)
         ret, outs = codec.process_batch(frames, xdm.MxnInArgsAlg(m, n))
         assert ret == 0, sensors.last_error()
@@ -131,10 +131,75 @@ def test_per_frame_grids_in_one_batch_through_the_table():
     grids = [(3, 3), (5, 5), (2, 7), (1, 1), (10, 10), (3, 3), (1, 20), (20, 1)]
     frames = np.stack([synth.make_frame("grid", s, w, h, "yuv422p", m=g[0], n=g[1]) for s, g in enumerate(grids)])
     ias = (xdm.MxnInArgsAlg * len(grids))(*[xdm.MxnInArgsAlg(*g) for g in grids])
-    lib().trikb200_setMxnTableMode(1)
-    ret, outs = codec.process_batch(frames, ias)
-    assert ret == 0
-    for i, (m, n) in enumerate(grids):
-        ok, exp = orc.process(frames[i], oracle.MxnInArgs(m, n))
-        assert list(outs[i].outColor[:m * n]) == list(exp.outColor[:m * n]), (i, m, n)
+    for mode in (0, 1):
+        lib().trikb200_setMxnTableMode(mode)
+        ret, outs = codec.process_batch(frames, ias)
+        assert ret == 0
+        for i, (m, n) in enumerate(grids):
+            ok, exp = orc.process(frames[i], oracle.MxnInArgs(m, n))
+            assert list(outs[i].outColor[:m * n]) == list(exp.outColor[:m * n]), (mode, i, m, n)
+    codec.close()
+
+
+def _majority_edge_frames(w, h, m, n):
+    """Cells in which the leading colour holds exactly half, one pixel more than half, and one pixel less than half of
+    the pixels (the majority pass may only decide the second), the rest one other colour or scattered colours."""
+    a, b = (60, 90, 200), (200, 180, 60)
+    hs, ws = h // m, w // n
+    out = []
+    for delta in (0, 1, -1, 2):
+        for scatter in (False, True):
+            y = np.full((h, w), b[0], np.uint8); u = np.full((h, w // 2), b[1], np.uint8); v = np.full((h, w // 2), b[2], np.uint8)
+            if scatter:
+                nz = synth.planes_noise(7 + delta, w, h)
+                y, u, v = nz[0].copy(), nz[1].copy(), nz[2].copy()
+            for i in range(m):
+                for j in range(n):
+                    r0, c0 = i * hs, (j * ws + 1) // 2 * 2                  # chroma pairs wholly inside the cell
+                    c1 = ((j + 1) * ws) // 2 * 2
+                    want = (hs * ws) // 2 + delta                           # pixels of colour a, whole pairs only
+                    pairs = max(0, min(want // 2, hs * ((c1 - c0) // 2)))
+                    k = 0
+                    for r in range(r0, r0 + hs):
+                        for c in range(c0, c1, 2):
+                            if k >= pairs:
+                                break
+                            y[r, c] = a[0]; y[r, c + 1] = a[0]; u[r, c // 2] = a[1]; v[r, c // 2] = a[2]
+                            k += 1
+            out.append(synth.pack(y, u, v, "yuv422p"))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("size,grid", [((320, 240), (3, 3)), ((640, 480), (3, 3)), ((160, 120), (2, 5)), ((320, 240), (4, 7))])
+def test_majority_pass_only_decides_what_it_can_prove(size, grid):
+    w, h = size
+    m, n = grid
+    codec = open_sensor("om", w, h)
+    orc = oracle.OracleSensor("om", w, h)
+    _check(codec, orc, _majority_edge_frames(w, h, m, n), m, n, ("majority-edge", size))
+    cam = np.stack([synth.make_frame("camera", s, w, h, "yuv422p", m=m, n=n) for s in range(3)])
+    _check(codec, orc, cam, m, n, ("camera", size))
+    codec.close()
+
+
+def test_majority_pass_one_cta_per_frame_and_back_to_back():
+    """Batches of >= 592 frames run the majority pass with one CTA per frame (all cell rows); the list of undecided cell
+    rows must be handed back empty, so a second and third batch on the same handle see no leftovers."""
+    w, h = 160, 120
+    codec = open_sensor("om", w, h)
+    orc = oracle.OracleSensor("om", w, h)
+    fams = [("grid", s) for s in range(10)] + [("noise", 1), ("scene", 3), ("halves", 0), ("camera", 2)]
+    for (m, n) in [(3, 3), (5, 5), (2, 7), (7, 1)]:
+        distinct = [synth.make_frame(f, s, w, h, "yuv422p", **({"m": m, "n": n} if f in ("grid", "camera") else {})) for f, s in fams]
+        want = []
+        for fr in distinct:
+            ok, exp = orc.process(fr, oracle.MxnInArgs(m, n))
+            want.append(list(exp.outColor[:m * n]))
+        frames = np.stack([distinct[i % len(distinct)] for i in range(640)])
+        lib().trikb200_setMxnTableMode(0)
+        for rep in range(3):
+            ret, outs = codec.process_batch(frames, xdm.MxnInArgsAlg(m, n))
+            assert ret == 0, sensors.last_error()
+            for i in range(640):
+                assert list(outs[i].outColor[:m * n]) == want[i % len(distinct)], (m, n, rep, i)
     codec.close()

@@ -133,6 +133,8 @@ struct Instance {
   uint8_t*     dClusters = nullptr; size_t dClustersCap = 0;   // OO cluster records (bytes)
   uint16_t*    dEqual = nullptr;    size_t dEqualCap = 0;      // OO label equivalences
   int*         dFlagged = nullptr;  size_t dFlaggedCap = 0;    // indices of frames that auto-calibrate
+  int*         dOmList = nullptr;   size_t dOmListCap = 0;     // OM: cell rows the majority pass left to the histogram kernel
+  int*         dOmCount = nullptr;  size_t dOmCountCap = 0;    // ... their number + a completion counter (self-resetting)
   int32_t*     dHist = nullptr;     size_t dHistCap = 0;       // ordered +1/-2 histograms (int32 entries)
   // chroma-indexed detection table of the last threshold set (WO batches, trik_kernels_lut.cu)
   uint8_t*     dLutTable = nullptr; uint32_t* dLutMasks = nullptr;
@@ -178,6 +180,8 @@ struct Instance {
     cudaFree(dClusters); dClusters = nullptr; dClustersCap = 0;
     cudaFree(dEqual);    dEqual = nullptr;    dEqualCap = 0;
     cudaFree(dFlagged);  dFlagged = nullptr;  dFlaggedCap = 0;
+    cudaFree(dOmList);   dOmList = nullptr;   dOmListCap = 0;
+    cudaFree(dOmCount);  dOmCount = nullptr;  dOmCountCap = 0;
     cudaFree(dHist);     dHist = nullptr;     dHistCap = 0;
     cudaFreeHost(hParams);  hParams = nullptr;  hParamsCap = 0;
     if (hParamsFree) { cudaEventDestroy(hParamsFree); hParamsFree = nullptr; }
@@ -679,8 +683,22 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
         // the colour bin is one fixed function of (Y,U,V): gather it from the device's 2^24-entry table (identical results)
         const uint16_t* binTable = ensure_om_table(in->device, s);
         if (!binTable) return false;
-        CUDA_TRY(launch_om_table(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,
-                                 reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s));
+        if (g_mxnTableMode == 0)
+        {
+          // majority pass first (a cell whose colour bin provably holds more than half of its pixels needs no
+          // histogram); the cell rows it leaves undecided go through the histogram kernel, taken from its list
+          if (!in->smCount)
+            CUDA_TRY(cudaDeviceGetAttribute(&in->smCount, cudaDevAttrMultiProcessorCount, in->device));
+          if (!in->grow_device(in->dOmList, in->dOmListCap, (size_t)b.n * maxRows, false)) return false;
+          if (!in->grow_device(in->dOmCount, in->dOmCountCap, 2, true)) return false;
+          CUDA_TRY(launch_om_major(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,
+                                   reinterpret_cast<int32_t*>(dOut), maxRows, in->dOmList, in->dOmCount, s));
+          CUDA_TRY(launch_om_table(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,
+                                   reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s, in->dOmList, in->dOmCount, in->smCount));
+        }
+        else
+          CUDA_TRY(launch_om_table(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,
+                                   reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s));
       }
       else
         CUDA_TRY(launch_om(g, b.n, dFrames, in->dParams, pstride, in->dMxnTable, reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s));

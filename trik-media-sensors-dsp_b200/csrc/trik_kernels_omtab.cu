@@ -107,17 +107,16 @@ __device__ __forceinline__ void hist_add(uint32_t addr, uint32_t cnt)
 //   * the hot loop counts only (dense 32-bank count arrays).  The reference's "first bin to reach the final maximum"
 //     (:434-440) needs the bins' last raster positions only to order bins whose FINAL counts tie at the maximum --
 //     rare -- so they are recovered afterwards, by a second pass over the cell row, only for such cells and bins.
-__global__ void __launch_bounds__(512, 2)
-om_table_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
-                const int paramStride, const uint16_t* __restrict__ table, const uint32_t* __restrict__ colorTable,
-                int32_t* __restrict__ out, const int maxGridRows, const int log2c)
+// one cell row of one frame, by the whole CTA
+__device__ __forceinline__ void
+om_table_item(const Geometry& g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+              const int paramStride, const uint16_t* __restrict__ table, const uint32_t* __restrict__ colorTable,
+              int32_t* __restrict__ out, const int frame, const int cellRow, const int log2c)
 {
   extern __shared__ uint32_t s_dyn[];      // [group + 1][512] counts (slot `group` is a sink), then [group][512] last positions
   __shared__ uint32_t s_tieMax[OMT_MAX_GROUP];            // per cell: the maximum count if several bins share it, else 0
   __shared__ uint32_t s_anyTie;
 
-  const int frame = blockIdx.x / maxGridRows;
-  const int cellRow = blockIdx.x - frame * maxGridRows;
   const FrameParams p = params[(size_t)frame * paramStride];
   const int M = (int)p.gridRows, N = (int)p.gridCols;
   if (cellRow >= M || N <= 0)
@@ -314,12 +313,48 @@ om_table_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
   }
 }
 
+__global__ void __launch_bounds__(512, 2)
+om_table_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+                const int paramStride, const uint16_t* __restrict__ table, const uint32_t* __restrict__ colorTable,
+                int32_t* __restrict__ out, const int maxGridRows, const int log2c)
+{
+  const int frame = blockIdx.x / maxGridRows;
+  om_table_item(g, frames, params, paramStride, table, colorTable, out, frame, blockIdx.x - frame * maxGridRows, log2c);
+}
+
+// The cell rows the majority pass (trik_kernels_ommaj.cu) could not decide: persistent CTAs take them from its list.
+// The last CTA to finish hands the list back empty, so back-to-back batches need no memset.
+__global__ void __launch_bounds__(512, 2)
+om_table_list_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+                     const int paramStride, const uint16_t* __restrict__ table, const uint32_t* __restrict__ colorTable,
+                     int32_t* __restrict__ out, const int maxGridRows, const int log2c,
+                     const int* __restrict__ list, int* __restrict__ listCount, int* __restrict__ done)
+{
+  const int n = *reinterpret_cast<volatile int*>(listCount);
+  for (int i = blockIdx.x; i < n; i += gridDim.x)
+  {
+    const int item = list[i];
+    const int frame = item / maxGridRows;
+    om_table_item(g, frames, params, paramStride, table, colorTable, out, frame, item - frame * maxGridRows, log2c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1)
+    {
+      *listCount = 0;
+      *done = 0;
+    }
+  }
+}
+
 static int g_omtWarps = 6;
 void set_om_table_threads(int threads) { g_omtWarps = threads > 0 ? (threads + 31) / 32 : 6; }
 
 cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                             int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
-                            int maxGridRows, int maxGridCols, cudaStream_t stream)
+                            int maxGridRows, int maxGridCols, cudaStream_t stream, const int* fbList, int* fbCount, int smCount)
 {
   if (numFrames <= 0 || maxGridRows <= 0)
     return cudaSuccess;
@@ -351,6 +386,23 @@ cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* fra
   if (smem > 48u * 1024u)
     cudaFuncSetAttribute(om_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (2 * OMT_MAX_GROUP + 1) * OMT_BINS * (int)sizeof(uint32_t));
+  if (fbList)
+  {
+    // list mode: only the cell rows the majority pass left undecided, by at most two CTAs per SM
+    if (smem > 48u * 1024u)
+      cudaFuncSetAttribute(om_table_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (2 * OMT_MAX_GROUP + 1) * OMT_BINS * (int)sizeof(uint32_t));
+    // as many CTAs as are resident at once (the histogram kernel lives on residency: ~14 KB of shared memory each)
+    int perSm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, om_table_list_kernel, warps * 32, smem) != cudaSuccess || perSm < 1)
+      perSm = 2;
+    const long long resident = (long long)perSm * smCount;
+    const unsigned ctas = (unsigned)(grid < resident ? grid : resident);
+    om_table_list_kernel<<<ctas, warps * 32, smem, stream>>>(g, frames, params, paramStride, table, colorTable, out,
+                                                            maxGridRows, log2c, fbList, fbCount, fbCount + 1);
+    ++g_launches_omtab;
+    return cudaGetLastError();
+  }
   om_table_kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(g, frames, params, paramStride, table, colorTable, out,
                                                                 maxGridRows, log2c);
   ++g_launches_omtab;
