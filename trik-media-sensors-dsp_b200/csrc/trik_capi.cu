@@ -134,7 +134,8 @@ struct Instance {
   uint16_t*    dEqual = nullptr;    size_t dEqualCap = 0;      // OO label equivalences
   int*         dFlagged = nullptr;  size_t dFlaggedCap = 0;    // indices of frames that auto-calibrate
   int*         dOmList = nullptr;   size_t dOmListCap = 0;     // OM: cell rows the majority pass left to the histogram kernel
-  int*         dOmCount = nullptr;  size_t dOmCountCap = 0;    // ... their number + a completion counter (self-resetting)
+  int*         dOmCount = nullptr;  size_t dOmCountCap = 0;    // ... their number: two counters, used by alternate batches
+  int          omParity = 0;
   int32_t*     dHist = nullptr;     size_t dHistCap = 0;       // ordered +1/-2 histograms (int32 entries)
   // chroma-indexed detection table of the last threshold set (WO batches, trik_kernels_lut.cu)
   uint8_t*     dLutTable = nullptr; uint32_t* dLutMasks = nullptr;
@@ -691,10 +692,13 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
             CUDA_TRY(cudaDeviceGetAttribute(&in->smCount, cudaDevAttrMultiProcessorCount, in->device));
           if (!in->grow_device(in->dOmList, in->dOmListCap, (size_t)b.n * maxRows, false)) return false;
           if (!in->grow_device(in->dOmCount, in->dOmCountCap, 2, true)) return false;
+          int* const cnt = in->dOmCount + in->omParity;                   // alternate batches use alternate counters:
+          int* const cntNext = in->dOmCount + (in->omParity ^ 1);         // each batch zeroes the one the next will use
+          in->omParity ^= 1;
           CUDA_TRY(launch_om_major(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,
-                                   reinterpret_cast<int32_t*>(dOut), maxRows, in->dOmList, in->dOmCount, s));
+                                   reinterpret_cast<int32_t*>(dOut), maxRows, in->dOmList, cnt, cntNext, s));
           CUDA_TRY(launch_om_table(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,
-                                   reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s, in->dOmList, in->dOmCount, in->smCount));
+                                   reinterpret_cast<int32_t*>(dOut), maxRows, maxCols, s, in->dOmList, cnt, in->smCount));
         }
         else
           CUDA_TRY(launch_om_table(g, b.n, dFrames, in->dParams, pstride, binTable, in->dMxnTable,

@@ -126,16 +126,17 @@ constexpr size_t OM_TABLE_BYTES = ((size_t)1 << 24) * sizeof(uint16_t);
 cudaError_t launch_om_bin_table(uint16_t* table, cudaStream_t stream);
 cudaError_t launch_om_table_probe(const uint16_t* table, uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
 // fbList != nullptr: only the cell rows listed there (items frame * maxGridRows + cellRow, *fbCount of them, written by
-// launch_om_major on the same stream); fbCount[0] = count, fbCount[1] = a completion counter, both left 0 again
+// launch_om_major on the same stream)
 cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                             int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
                             int maxGridRows, int maxGridCols, cudaStream_t stream,
-                            const int* fbList = nullptr, int* fbCount = nullptr, int smCount = 148);
+                            const int* fbList = nullptr, const int* fbCount = nullptr, int smCount = 148);
 // OM majority pass (trik_kernels_ommaj.cu): decides every cell in which one colour bin provably holds more than half of
-// the pixels, and lists the cell rows with an undecided cell in fbList / fbCount for launch_om_table's list mode
+// the pixels, and lists the cell rows with an undecided cell in fbList / fbCount for launch_om_table's list mode;
+// *fbCount must be 0 at launch, *fbCountNext (the counter the NEXT batch will use) is zeroed by this launch
 cudaError_t launch_om_major(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                             int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
-                            int maxGridRows, int* fbList, int* fbCount, cudaStream_t stream);
+                            int maxGridRows, int* fbList, int* fbCount, int* fbCountNext, cudaStream_t stream);
 void set_om_table_threads(int threads);
 void set_lut_skew(int on);
 // RGB565 -> YUV422P ingest front end (trik_kernels_ingest.cu)

@@ -10,10 +10,11 @@
 //     if a bin holds MORE THAN HALF of a cell's pixels it is the unique maximum, hence "the first to reach the final
 //     maximum", whatever the other pixels are and in whatever order they come.
 //
-// So this pass only PROVES a majority, with a lower bound that costs three instructions per pixel and no gather:
-//   1. per cell, 16 sample pixels vote for a candidate (chroma pair, colour bin) -- the only table gathers of the pass;
-//   2. the table row of that chroma pair ([U][V][0..255], 512 bytes, one coalesced read) gives the luma interval
-//      lo..hi around the sample's luma on which the bin is the candidate's;
+// So this pass only PROVES a majority, with a lower bound that costs four instructions per pixel and no gather:
+//   1. per cell, 16 sample pixels vote for a candidate chroma pair;
+//   2. the table row of that chroma pair ([U][V][0..255], 512 bytes, one coalesced read -- the only table access of the
+//      pass) gives the candidate bin (the one of a voter's luma) and the luma interval lo..hi around it on which the
+//      row holds that bin;
 //   3. the cell's pixels are streamed once (16 pixels per thread and row, cp.async ring as the line kernels) and those
 //      with exactly the candidate's chroma and a luma inside lo..hi are counted -- each of them IS in the candidate's
 //      bin, so the count is a lower bound of that bin's count;
@@ -22,6 +23,7 @@
 // Bit-identical by construction: the shortcut is only taken where it is a proof.  Frames it cannot serve (noise, chroma
 // noise, cells of several colours, cells narrower than 16 pixels) cost the samples and then take the histogram path.
 #include <atomic>
+#include <cstdlib>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 
@@ -29,33 +31,51 @@ namespace trikb200 {
 
 extern std::atomic<long long> g_launches_omtab;
 
-constexpr int OMJ_STAGES = 4;
 constexpr int OMJ_MAX_CELLS = 100;           // widthM * heightN <= 100 (outColor[100])
 constexpr int OMJ_MIN_VOTES = 6;             // of 16 samples: below that a cell is not worth streaming for
 
 struct OmjCand {
   uint32_t half;                             // chroma half-word V | U << 8 as it lies in the plane
-  uint32_t negLo;                            // (-lo) mod 2^16; lo = 256 (nothing passes) for a cell without candidate
-  uint32_t span;                             // hi - lo
+  uint32_t lo;                               // luma interval lo..hi; lo = 256 (nothing passes) for a cell without candidate
+  uint32_t nhi;                              // 255 - hi
   uint32_t bin4;                             // table entry of the candidate: bin * 4
 };
+
+// a * b + c on the FMA pipe (IMAD), also where b is 1: the ALU pipe is the busy one in this kernel
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+__device__ __forceinline__ uint32_t madhi_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t d;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 
 __device__ __forceinline__ void omj_push(int* __restrict__ list, int* __restrict__ count, int item)
 {
   list[atomicAdd(count, 1)] = item;
 }
 
-__global__ void __launch_bounds__(256, 3)
+template <int OMJ_STAGES, int MINB>
+__global__ void __launch_bounds__(192, MINB)
 om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
                 const int paramStride, const uint16_t* __restrict__ table, const uint32_t* __restrict__ colorTable,
                 int32_t* __restrict__ out, const int maxGridRows, const int cellRowsPerCta, const int ctasPerFrame,
-                const int cpr, const int rpi, int* __restrict__ fbList, int* __restrict__ fbCount)
+                const int cpr, const int rpi, int* __restrict__ fbList, int* __restrict__ fbCount, int* __restrict__ fbCountNext,
+                const uint32_t one, const uint32_t minusOne, const uint32_t k17)     // 1, -1, 1 << 17: multipliers the compiler cannot fold
 {
   __shared__ OmjCand s_cand[OMJ_MAX_CELLS];
   __shared__ uint32_t s_count[OMJ_MAX_CELLS];
   __shared__ uint32_t s_rowBad[OMJ_MAX_CELLS];
   extern __shared__ uint4 s_ring[];            // [STAGES][2][blockDim]: luma chunk, chroma chunk
 
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    *fbCountNext = 0;                                     // the counter of the previous batch (drained, by stream order)
   const int frame = blockIdx.x / ctasPerFrame;
   const int part = blockIdx.x - frame * ctasPerFrame;
   const FrameParams p = params[(size_t)frame * paramStride];
@@ -122,19 +142,21 @@ om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
       const uint8_t* ptr = fbase + (size_t)row * g.lineLength;
       const uint32_t y = ptr[col];
       const uint32_t half = *reinterpret_cast<const uint16_t*>(ptr + chromaOfs + (col & ~1));
-      const uint32_t e = __ldg(table + ((half << 8) | y));
-      const unsigned peers = __match_any_sync(hmask, (half << 16) | e) & hmask;
-      const int votes = __popc(peers);
-      const int best = __reduce_max_sync(hmask, votes);
-      const int owner = __ffs((int)(__ballot_sync(hmask, votes == best) & hmask)) - 1;
+      // the samples vote for a chroma pair; the luma of one of its voters and the table row of that pair then give the
+      // candidate bin and its luma interval in ONE further round trip
+      // (among the voters of the winning chroma pair, one whose luma is the most common: not an outlier's)
+      const int votes = __popc(__match_any_sync(hmask, half) & hmask);
+      const int score = votes * 32 + __popc(__match_any_sync(hmask, (half << 8) | y) & hmask);
+      const int bestScore = __reduce_max_sync(hmask, score);
+      const int best = bestScore >> 5;
+      const int owner = __ffs((int)(__ballot_sync(hmask, score == bestScore) & hmask)) - 1;
       const uint32_t cHalf = __shfl_sync(hmask, half, owner);
-      const uint32_t cE = __shfl_sync(hmask, e, owner);
       const int cY = (int)__shfl_sync(hmask, y, owner);
       OmjCand cand;
-      cand.half = cHalf; cand.bin4 = cE;
+      cand.half = cHalf; cand.bin4 = 0u;
       if (best < OMJ_MIN_VOTES)
       {
-        cand.negLo = (0x10000u - 256u) & 0xFFFFu; cand.span = 0u;        // lo = 256: no luma passes
+        cand.lo = 256u; cand.nhi = 0u;                                     // lo = 256: no luma passes
         if (l16 == 0)
           s_rowBad[cell / N] = 1u;
       }
@@ -143,6 +165,8 @@ om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
         // the luma interval around cY on which the candidate chroma's table row holds the candidate bin
         const uint4* rowp = reinterpret_cast<const uint4*>(table + ((size_t)cHalf << 8)) + 2 * l16;
         const uint4 v0 = __ldg(rowp), v1 = __ldg(rowp + 1);
+        const uint32_t cE = __ldg(table + (((size_t)cHalf << 8) | (uint32_t)cY));
+        cand.bin4 = cE;
         const uint32_t wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         uint32_t eq = 0u;
 #pragma unroll
@@ -160,8 +184,8 @@ om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
         const int zhi = za ? basePos + __ffs((int)za) - 1 : 256;
         const int lo = __reduce_max_sync(hmask, zlo) + 1;
         const int hi = __reduce_min_sync(hmask, zhi) - 1;
-        cand.negLo = (0x10000u - (uint32_t)lo) & 0xFFFFu;
-        cand.span = (uint32_t)(hi - lo);
+        cand.lo = (uint32_t)lo;
+        cand.nhi = (uint32_t)(255 - hi);
       }
       if (l16 == 0)
         s_cand[cell] = cand;
@@ -195,28 +219,31 @@ om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
     if (nIt <= 0)
       continue;
     OmjCand a, b;
-    a.half = 0u; a.negLo = (0x10000u - 256u) & 0xFFFFu; a.span = 0u; a.bin4 = 0u;
+    a.half = 0u; a.lo = 256u; a.nhi = 0u; a.bin4 = 0u;
     b = a;
     if (cA < N) a = s_cand[(cr - cr0) * N + cA];
     if (cA + 1 < N) b = s_cand[(cr - cr0) * N + cA + 1];
     // per luma word w (pixels 4w .. 4w+3, chroma pairs 2w and 2w+1): the pair's candidate chroma is that of its EVEN
-    // pixel's cell; an odd pixel whose cell differs from its pair's (odd cell width) is not counted -- a lower bound stays one
-    uint32_t candW[4], negLoE[4], nE[4], negLoO[4], nO[4];
+    // pixel's cell; an odd pixel whose cell differs from its pair's (odd cell width) is not counted -- a lower bound stays one.
+    // With yG = 0x8000 + Y per lane:  yG - lo2  and  hiG - Y2 = (0x80008000 + hi2) - (yG - 0x80008000) = C - yG  with
+    // C = 0x010000FF - nhi2 (mod 2^32; hi2 = 0x00FF00FF - nhi2, and twice the guard is 0x1_0001_0000) are one multiply-add
+    // each, and exact: every RESULT lane lies in 0x7F00 .. 0x80FF, so no lane borrows from its neighbour whatever the
+    // intermediate sums look like.
+    uint32_t candW[4], mLoE[4], mHiE[4], mLoO[4], mHiO[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w)
     {
       const bool e0A = 4 * w < split, e1A = 4 * w + 2 < split;              // even pixels 4w, 4w+2
       const bool o0A = 4 * w + 1 < split, o1A = 4 * w + 3 < split;          // odd pixels 4w+1, 4w+3
       candW[w] = (e0A ? a.half : b.half) | ((e1A ? a.half : b.half) << 16);
-      negLoE[w] = (e0A ? a.negLo : b.negLo) | ((e1A ? a.negLo : b.negLo) << 16);
-      nE[w] = (e0A ? a.span : b.span) | ((e1A ? a.span : b.span) << 16);
-      const uint32_t nullLo = (0x10000u - 256u) & 0xFFFFu;
-      const uint32_t lo0 = o0A == e0A ? (o0A ? a.negLo : b.negLo) : nullLo, lo1 = o1A == e1A ? (o1A ? a.negLo : b.negLo) : nullLo;
-      const uint32_t n0 = o0A == e0A ? (o0A ? a.span : b.span) : 0u, n1 = o1A == e1A ? (o1A ? a.span : b.span) : 0u;
-      negLoO[w] = lo0 | (lo1 << 16);
-      nO[w] = n0 | (n1 << 16);
+      mLoE[w] = 0u - ((e0A ? a.lo : b.lo) | ((e1A ? a.lo : b.lo) << 16));
+      mHiE[w] = 0x010000FFu - ((e0A ? a.nhi : b.nhi) | ((e1A ? a.nhi : b.nhi) << 16));
+      const uint32_t lo0 = o0A == e0A ? (o0A ? a.lo : b.lo) : 256u, lo1 = o1A == e1A ? (o1A ? a.lo : b.lo) : 256u;
+      const uint32_t h0 = o0A == e0A ? (o0A ? a.nhi : b.nhi) : 0u, h1 = o1A == e1A ? (o1A ? a.nhi : b.nhi) : 0u;
+      mLoO[w] = 0u - (lo0 | (lo1 << 16));
+      mHiO[w] = 0x010000FFu - (h0 | (h1 << 16));
     }
-    uint32_t accE[4] = {0u, 0u, 0u, 0u}, accO[4] = {0u, 0u, 0u, 0u};
+    uint32_t accE[4] = {0u, 0u, 0u, 0u}, accO[4] = {0u, 0u, 0u, 0u};        // passes per pixel position, two 16-bit lanes each
 #pragma unroll 2
     for (int it = 0; it < nIt; ++it, ++git)
     {
@@ -234,18 +261,20 @@ om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
 #pragma unroll
       for (int w = 0; w < 4; ++w)
       {
-        // 0xFFFF in the lane of a pair whose chroma is not the candidate's: pushes that lane over its span below
-        const uint32_t m = __vminu2(Cw[w] ^ candW[w], 0x00010001u) * 0xFFFFu;
-        const uint32_t yE = __byte_perm(L[w], 0u, 0x4240);                  // lumas of pixels 4w, 4w+2
-        const uint32_t yO = __byte_perm(L[w], 0u, 0x4341);                  // ... 4w+1, 4w+3
-        // (Y - lo) mod 2^16 <= span  <=>  inside lo..hi;  lanes end up {span, span+1} = {inside, not}
-        const uint32_t uE = __vimax3_u16x2(__vadd2(yE, negLoE[w]), nE[w], m);
-        const uint32_t uO = __vimax3_u16x2(__vadd2(yO, negLoO[w]), nO[w], m);
-        accE[w] = __vadd2(accE[w], __vminu2(uE, nE[w] + 0x00010001u));
-        accO[w] = __vadd2(accO[w], __vminu2(uO, nO[w] + 0x00010001u));
+        // The work is split between the two integer pipes (each issues one warp instruction per two cycles): byte
+        // permutes and logic on the ALU pipe, the compares and the counting as multiply-adds on the FMA pipe.
+        // eqG: guard bit 15 in the lane of a pair whose chroma IS the candidate's
+        const uint32_t eqG = mad_u32(__vminu2(Cw[w] ^ candW[w], 0x00010001u), 0xFFFF8000u, 0x80008000u);
+        const uint32_t yE = __byte_perm(L[w], 0x80808080u, 0x4240);         // 0x8000 + Y of pixels 4w, 4w+2
+        const uint32_t yO = __byte_perm(L[w], 0x80808080u, 0x4341);         // ... 4w+1, 4w+3
+        // bit 15 of a lane stays set <=> Y >= lo (guard + Y - lo), resp. Y <= hi (guard + hi - Y, as C - (guard + Y))
+        const uint32_t xE = mad_u32(yE, one, mLoE[w]) & mad_u32(yE, minusOne, mHiE[w]) & eqG;
+        const uint32_t xO = mad_u32(yO, one, mLoO[w]) & mad_u32(yO, minusOne, mHiO[w]) & eqG;
+        accE[w] = madhi_u32(xE, k17, accE[w]);                              // bit 15 -> +1 in lane 0, bit 31 -> +1 in lane 1
+        accO[w] = madhi_u32(xO, k17, accO[w]);
       }
     }
-    // passes per pixel position = nIt - ((acc - nIt * span) mod 2^16); pixels left of `split` count for A, the others for B
+    // pixels left of `split` count for cell A, the others for B
     uint32_t cntA = 0u, cntB = 0u;
 #pragma unroll
     for (int w = 0; w < 4; ++w)
@@ -253,10 +282,7 @@ om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
 #pragma unroll
       for (int h = 0; h < 2; ++h)                                           // lane h: even pixel 4w + 2h, odd pixel 4w + 2h + 1
       {
-        const uint32_t sE = (nE[w] >> (16 * h)) & 0xFFFFu, sO = (nO[w] >> (16 * h)) & 0xFFFFu;
-        const uint32_t fE = (((accE[w] >> (16 * h)) & 0xFFFFu) - (uint32_t)nIt * sE) & 0xFFFFu;
-        const uint32_t fO = (((accO[w] >> (16 * h)) & 0xFFFFu) - (uint32_t)nIt * sO) & 0xFFFFu;
-        const uint32_t pE = (uint32_t)nIt - fE, pO = (uint32_t)nIt - fO;
+        const uint32_t pE = (accE[w] >> (16 * h)) & 0xFFFFu, pO = (accO[w] >> (16 * h)) & 0xFFFFu;
         if (4 * w + 2 * h < split) cntA += pE; else cntB += pE;
         if (4 * w + 2 * h + 1 < split) cntA += pO; else cntB += pO;
       }
@@ -284,33 +310,48 @@ om_major_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
 
 cudaError_t launch_om_major(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                             int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
-                            int maxGridRows, int* fbList, int* fbCount, cudaStream_t stream)
+                            int maxGridRows, int* fbList, int* fbCount, int* fbCountNext, cudaStream_t stream)
 {
   if (numFrames <= 0 || maxGridRows <= 0)
     return cudaSuccess;
   const int cpr = g.width / 16;
-  if (cpr <= 0 || cpr > 256)
+  if (cpr <= 0 || cpr > 192)
     return cudaErrorInvalidValue;
   // ~160 threads, a whole number of rows per iteration, whole warps when that is possible
-  int rpi = (160 + cpr - 1) / cpr;
+  static const int targetThreads = getenv("TRIKB200_OMJ_THREADS") ? atoi(getenv("TRIKB200_OMJ_THREADS")) : 160;
+  int rpi = (targetThreads + cpr - 1) / cpr;
   for (int j = 0; j < 16; ++j)
-    if ((cpr * (rpi + j)) % 32 == 0 && cpr * (rpi + j) <= 256)
+    if ((cpr * (rpi + j)) % 32 == 0 && cpr * (rpi + j) <= 192)
     {
       rpi += j;
       break;
     }
-  while (cpr * rpi > 256) --rpi;
+  while (cpr * rpi > 192) --rpi;
   if (rpi < 1) rpi = 1;
   const int threads = cpr * rpi;
   // one CTA per frame once the frames alone fill the machine, else one per cell row
-  const int cellRowsPerCta = numFrames >= 148 * 4 ? maxGridRows : 1;
+  // (whole frames amortise the candidate search better, but the grid should still be five or more waves of CTAs)
+  static const int perFrameFrom = getenv("TRIKB200_OMJ_PER_FRAME_FROM") ? atoi(getenv("TRIKB200_OMJ_PER_FRAME_FROM")) : 148 * 4 * 5;
+  const int cellRowsPerCta = numFrames >= perFrameFrom ? maxGridRows : 1;
   const int ctasPerFrame = (maxGridRows + cellRowsPerCta - 1) / cellRowsPerCta;
   const long long grid = (long long)numFrames * ctasPerFrame;
   if (grid > 0x7FFFFFFFLL)
     return cudaErrorInvalidValue;
-  const size_t smem = (size_t)OMJ_STAGES * 2 * 16 * threads;
-  om_major_kernel<<<(unsigned)grid, threads, smem, stream>>>(g, frames, params, paramStride, table, colorTable, out,
-                                                            maxGridRows, cellRowsPerCta, ctasPerFrame, cpr, rpi, fbList, fbCount);
+  static const int stages = getenv("TRIKB200_OMJ_STAGES") ? atoi(getenv("TRIKB200_OMJ_STAGES")) : 4;
+  static const int minb = getenv("TRIKB200_OMJ_MINB") ? atoi(getenv("TRIKB200_OMJ_MINB")) : 4;
+  const size_t smem = (size_t)stages * 2 * 16 * threads;
+#define OMJ_LAUNCH(S, B)                                                                                                     \
+  do {                                                                                                                       \
+    if (smem > 48u * 1024u)                                                                                                  \
+      cudaFuncSetAttribute(om_major_kernel<S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
+    om_major_kernel<S, B><<<(unsigned)grid, threads, smem, stream>>>(g, frames, params, paramStride, table, colorTable, out, \
+                                                                     maxGridRows, cellRowsPerCta, ctasPerFrame, cpr, rpi,    \
+                                                                     fbList, fbCount, fbCountNext, 1u, 0xFFFFFFFFu, 1u << 17);            \
+  } while (0)
+  if (stages == 8) { if (minb >= 5) OMJ_LAUNCH(8, 5); else if (minb == 4) OMJ_LAUNCH(8, 4); else OMJ_LAUNCH(8, 3); }
+  else if (stages == 6) { if (minb >= 5) OMJ_LAUNCH(6, 5); else if (minb == 4) OMJ_LAUNCH(6, 4); else OMJ_LAUNCH(6, 3); }
+  else { if (minb >= 5) OMJ_LAUNCH(4, 5); else if (minb == 4) OMJ_LAUNCH(4, 4); else OMJ_LAUNCH(4, 3); }
+#undef OMJ_LAUNCH
   ++g_launches_omtab;
   return cudaGetLastError();
 }

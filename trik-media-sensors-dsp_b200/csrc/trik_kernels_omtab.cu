@@ -19,6 +19,8 @@
 // Bit-identical to om_kernel by construction (the table IS that arithmetic); tests/test_omtab_gpu.py compares the
 // table with the oracle on all 2^24 inputs and the sensor through both paths with the oracle on frames.
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 
@@ -323,29 +325,19 @@ om_table_kernel(const Geometry g, const uint8_t* __restrict__ frames, const Fram
 }
 
 // The cell rows the majority pass (trik_kernels_ommaj.cu) could not decide: persistent CTAs take them from its list.
-// The last CTA to finish hands the list back empty, so back-to-back batches need no memset.
+// (The list counters are two, used by alternate batches; the majority pass zeroes the one it does not use.)
 __global__ void __launch_bounds__(512, 2)
 om_table_list_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
                      const int paramStride, const uint16_t* __restrict__ table, const uint32_t* __restrict__ colorTable,
                      int32_t* __restrict__ out, const int maxGridRows, const int log2c,
-                     const int* __restrict__ list, int* __restrict__ listCount, int* __restrict__ done)
+                     const int* __restrict__ list, const int* __restrict__ listCount)
 {
-  const int n = *reinterpret_cast<volatile int*>(listCount);
+  const int n = *listCount;
   for (int i = blockIdx.x; i < n; i += gridDim.x)
   {
     const int item = list[i];
     const int frame = item / maxGridRows;
     om_table_item(g, frames, params, paramStride, table, colorTable, out, frame, item - frame * maxGridRows, log2c);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    __threadfence();
-    if (atomicAdd(done, 1) == (int)gridDim.x - 1)
-    {
-      *listCount = 0;
-      *done = 0;
-    }
   }
 }
 
@@ -354,7 +346,7 @@ void set_om_table_threads(int threads) { g_omtWarps = threads > 0 ? (threads + 3
 
 cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                             int paramStride, const uint16_t* table, const uint32_t* colorTable, int32_t* out,
-                            int maxGridRows, int maxGridCols, cudaStream_t stream, const int* fbList, int* fbCount, int smCount)
+                            int maxGridRows, int maxGridCols, cudaStream_t stream, const int* fbList, const int* fbCount, int smCount)
 {
   if (numFrames <= 0 || maxGridRows <= 0)
     return cudaSuccess;
@@ -392,6 +384,14 @@ cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* fra
     if (smem > 48u * 1024u)
       cudaFuncSetAttribute(om_table_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (2 * OMT_MAX_GROUP + 1) * OMT_BINS * (int)sizeof(uint32_t));
+    static const bool debugList = getenv("TRIKB200_OMJ_DEBUG") != nullptr;       // diagnostics: how long is the list?
+    if (debugList)
+    {
+      int c = -1;
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(&c, fbCount, sizeof(c), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "om list: %d of %lld cell rows undecided\n", c, grid);
+    }
     // as many CTAs as are resident at once (the histogram kernel lives on residency: ~14 KB of shared memory each)
     int perSm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, om_table_list_kernel, warps * 32, smem) != cudaSuccess || perSm < 1)
@@ -399,7 +399,7 @@ cudaError_t launch_om_table(const Geometry& g, int numFrames, const uint8_t* fra
     const long long resident = (long long)perSm * smCount;
     const unsigned ctas = (unsigned)(grid < resident ? grid : resident);
     om_table_list_kernel<<<ctas, warps * 32, smem, stream>>>(g, frames, params, paramStride, table, colorTable, out,
-                                                            maxGridRows, log2c, fbList, fbCount, fbCount + 1);
+                                                            maxGridRows, log2c, fbList, fbCount);
     ++g_launches_omtab;
     return cudaGetLastError();
   }
