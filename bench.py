@@ -557,6 +557,15 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, e2e_steps)
 
+    # the ceiling of that leg on THIS box at THIS N: the same pinned buffer through plain cudaMemcpyAsync on every rank at
+    # the same time (no kernels, no results), timed the same way -- what the host / PCIe side can deliver to N GPUs at once
+    def step_h2d():
+        d_frames.copy_(host, non_blocking=True)
+
+    for _ in range(2):
+        step_h2d()
+    ms_h2d = timed(step_h2d, e2e_steps)
+
     mixed = None
     if not args.no_mixed:
         mixed = config4_mixed(args, torch, dist, dev, rank, world)
@@ -582,7 +591,12 @@ def main():
                          "peak_source": peak_src, "kernel": "vsum_kernel<YUYV> (WL)",
                          "algorithmic_bytes_per_launch": algo_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * fbytes, "d2h_bytes_per_step": n * rec,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps,
+                    "h2d_gbs": world * n * fbytes / (ms_e2e / e2e_steps / 1000.0) / 1e9,
+                    "h2d_ceiling_gbs": world * n * fbytes / (ms_h2d / e2e_steps / 1000.0) / 1e9,
+                    "frac_of_h2d_ceiling": ms_h2d / ms_e2e,
+                    "h2d_ceiling": "plain pinned cudaMemcpyAsync of the same %.0f MB on all %d rank(s) concurrently, same timing"
+                                   % (n * fbytes / 1e6, world)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "repeat_ms_per_step": [r / args.steps for r in runs],

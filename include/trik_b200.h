@@ -224,10 +224,26 @@ typedef struct TRIKB200_Batch {
  * nothing written to outArgsAlg. */
 XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Batch* batch);
 
+/* The same over several GPUs of one box (frames shard by batch, no collective on the per-pixel path):
+ * handles[0..numHandles) are distinct instances of ONE sensor kind and geometry, each created after
+ * trikb200_setDevice(d) for the device it shall run on (two handles may share a device).  The batch is cut into
+ * numHandles contiguous frame ranges, range d runs on handles[d] from its own host thread and stream, and every
+ * result lands in the caller's one outArgsAlg array.  Carried state (ov7670 line sensor band, object sensor range)
+ * is walked over the whole batch first, so the results are those of numFrames sequential process() calls on
+ * handles[0]; afterwards every handle holds the state after the last frame.  Host frames / results / previews
+ * only, synchronous, no caller stream, no streamIds (IVIDTRANSCODE_EFAIL otherwise).  Replaces N instances of the
+ * reference's codec behind N Codec Engine servers (dsp_server/server.cfg:139-142). */
+XDAS_Int32 trikb200_processBatchMulti(const IVIDTRANSCODE_Handle* handles, XDAS_Int32 numHandles,
+                                      const TRIKB200_Batch* batch);
+
 /* Mixed sensors in one call (BASELINE.json config 4: line + object + mxn instances over many streams):
  * a table of {handle, frame} pairs with HOST frames.  Entries of one handle are processed in table order
- * (== sequential process() calls on that handle); different handles run concurrently on their own CUDA
- * streams.  seed: srand() seed for an annealed auto-detect (negative = time(NULL)). */
+ * (== sequential process() calls on that handle).  Handles of the same sensor kind, device and geometry
+ * (the reference's model is one codec instance per camera, dsp_server/server.cfg:139-142) share ONE launch
+ * per kernel, each frame judged with the carried state of its own handle; the classes run concurrently on
+ * their own CUDA streams.  Pinned (cudaHostAlloc / cudaHostRegister) frames are read in place by one gather
+ * kernel per class, pageable ones go through one copy per frame (neighbours in memory merged).
+ * seed: srand() seed for an annealed auto-detect (negative = time(NULL)). */
 typedef struct TRIKB200_MixedEntry {
     IVIDTRANSCODE_Handle handle;
     const void*          frame;       /* host pointer to one frame of the handle's geometry */
@@ -328,6 +344,9 @@ void trikb200_setLutMode(XDAS_Int32 mode);
  * without a histogram -- and the table-gather histogram kernel for the cell rows that leaves undecided;
  * 1 = the histogram kernel for every cell row; -1 = no table at all (arithmetic kernel) */
 void trikb200_setMxnTableMode(XDAS_Int32 mode);
+/* tuning knob: scattered frames of trikb200_processMixed: 0 (default) = pinned host frames are read in place by one gather
+ * kernel per class from 8 frames up, 1 = from one frame up, -1 = always one cudaMemcpyAsync per frame */
+void trikb200_setGatherMode(XDAS_Int32 mode);
 /* tuning knob: 1 (default) = the shared-memory detection table of the object sensors is laid out with skewed rows (260
  * instead of 256 bytes apart): no bank conflicts when the chroma of neighbouring pixels differs by a little (camera noise),
  * for one more instruction per pixel pair (+60..75 % on such frames, -4 % on frames with noise-free chroma); 0 = plain rows */

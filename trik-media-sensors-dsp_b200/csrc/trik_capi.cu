@@ -29,6 +29,7 @@ thread_local int t_device = -1;
 int g_slabsPerFrame = 0;
 int g_zeroCopyBytes = 1 << 20;     // synchronous host batches up to this many frame bytes go through the handle's pinned staging
 int g_lutMode = 0;                 // 0 auto, 1 whenever the arguments are shared by the batch, -1 never
+int g_gatherMode = 0;              // scattered pinned host frames: 0 auto (gather kernel from 8 frames), 1 always, -1 never (one copy per frame)
 int g_mxnTableMode = 0;            // mxn sensor through the colour-bin table: 0 / 1 yes (default), -1 never (arithmetic kernel)
 
 // The colour-bin table of the mxn sensor (trik_kernels_omtab.cu) depends on nothing but the device: built once per
@@ -156,6 +157,11 @@ struct Instance {
   uint8_t*     hFrames = nullptr;   size_t hFramesCap = 0;     // small host batches: frames staged here, read in place by the kernels
   uint8_t*     hPreview = nullptr;  size_t hPreviewCap = 0;    // ... and previews written here by the kernels
   int*         hFlagged = nullptr;  size_t hFlaggedCap = 0;
+  const uint8_t** hPtrs = nullptr;  size_t hPtrsCap = 0;       // scattered frames: their device-visible addresses, staged ...
+  const uint8_t** dPtrs = nullptr;  size_t dPtrsCap = 0;       // ... and on the device for the gather kernel
+  cudaEvent_t  hPtrsFree = nullptr;                            // completes when the last upload has read hPtrs
+  // a threshold set that keeps coming back in medium-sized batches is worth its chroma table
+  uint32_t     lutSeenFrom = 0, lutSeenTo = 0, lutSeenExpected = 0; int lutSeenCount = 0;
   uint32_t*    hSeeds = nullptr;    size_t hSeedsCap = 0;      // device annealing tail: one seed per calibrating frame
   uint32_t*    dSeeds = nullptr;    size_t dSeedsCap = 0;
   cudaEvent_t  hStageFree = nullptr;                           // completes when hFlagged / hSeeds have been read
@@ -191,6 +197,9 @@ struct Instance {
     cudaFreeHost(hFrames);  hFrames = nullptr;  hFramesCap = 0;
     cudaFreeHost(hPreview); hPreview = nullptr; hPreviewCap = 0;
     cudaFreeHost(hFlagged); hFlagged = nullptr; hFlaggedCap = 0;
+    cudaFreeHost(hPtrs);    hPtrs = nullptr;    hPtrsCap = 0;
+    cudaFree(dPtrs);        dPtrs = nullptr;    dPtrsCap = 0;
+    if (hPtrsFree) { cudaEventDestroy(hPtrsFree); hPtrsFree = nullptr; }
     cudaFreeHost(hHist);    hHist = nullptr;    hHistCap = 0;
     cudaFreeHost(hSeeds);   hSeeds = nullptr;   hSeedsCap = 0;
     cudaFree(dSeeds); dSeeds = nullptr; dSeedsCap = 0;
@@ -347,6 +356,7 @@ struct BatchView {
   const uint8_t* const* framePtrs = nullptr;
   const uint8_t* const* inPtrs = nullptr;
   uint8_t* const*       outPtrs = nullptr;
+  CarriedState* const*  statePtrs = nullptr;   // per frame: the carried state of the handle the frame belongs to
 
   const uint8_t* in_args(int i) const { return inPtrs ? inPtrs[i] : inArgs + (size_t)i * inStride; }
   uint8_t* out_args(int i) const { return outPtrs ? outPtrs[i] : outArgs + (size_t)i * outStride; }
@@ -454,6 +464,20 @@ bool is_pinned_host(const void* p)
   return attr.type == cudaMemoryTypeHost;
 }
 
+// Batches of 32..255 frames do not pay for a table on their own; the third one in a row under the same threshold set
+// does (a camera rig calling once per time step).
+bool lut_set_recurs(Instance* in, const FrameParams& fp)
+{
+  if (in->lutSeenCount > 0 && in->lutSeenFrom == fp.from && in->lutSeenTo == fp.to && in->lutSeenExpected == fp.expected)
+    ++in->lutSeenCount;
+  else
+  {
+    in->lutSeenFrom = fp.from; in->lutSeenTo = fp.to; in->lutSeenExpected = fp.expected;
+    in->lutSeenCount = 1;
+  }
+  return in->lutSeenCount >= 3;
+}
+
 // build (or keep) the chroma table of a threshold set on stream s
 bool ensure_lut(Instance* in, const FrameParams& fp, bool have, cudaStream_t s)
 {
@@ -539,17 +563,33 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
   (void)inSize;
 
   // 1. per-frame parameters (carried state advances frame by frame, as n process() calls would)
-  const bool broadcast = b.broadcast_in() && kind != KIND_OL && kind != KIND_OO;
+  bool broadcast = b.broadcast_in() && kind != KIND_OL && kind != KIND_OO;
   if (b.streamIds && (int)in->streamStates.size() < b.numStreams)
     in->streamStates.resize((size_t)b.numStreams);
-  const size_t np = broadcast ? 1 : (size_t)b.n;
+  size_t np = broadcast ? 1 : (size_t)b.n;
+  in->paramsScratch.assign(np, FrameParams{});
+  for (size_t i = 0; i < np; ++i)
+    prepare_frame_params(kind, in->geo, b.in_args((int)i),
+                         b.statePtrs ? *b.statePtrs[i] : b.streamIds ? in->streamStates[(size_t)b.streamIds[i]] : in->state,
+                         in->paramsScratch[i]);
+  // A per-frame array (or pointer list) of arguments that all say the same thing is a broadcast: one record, and the
+  // chroma-table path of the webcam object sensor stays available (a batch gathered from many handles looks like this).
+  if (!broadcast && (kind == KIND_WO || kind == KIND_WL) && np > 1)
+  {
+    bool same = true;
+    for (size_t i = 1; same && i < np; ++i)
+      same = std::memcmp(&in->paramsScratch[0], &in->paramsScratch[i], sizeof(FrameParams)) == 0;
+    if (same)
+    {
+      broadcast = true;
+      np = 1;
+      in->paramsScratch.resize(1);
+    }
+  }
   const FrameParams* const dParamsBefore = in->dParams;
   if (!in->grow_device(in->dParams, in->dParamsCap, np, false)) return false;
   if (in->dParams != dParamsBefore)
     in->dBroadcastValid = false;
-  in->paramsScratch.assign(np, FrameParams{});
-  for (size_t i = 0; i < np; ++i)
-    prepare_frame_params(kind, in->geo, b.in_args((int)i), b.streamIds ? in->streamStates[(size_t)b.streamIds[i]] : in->state, in->paramsScratch[i]);
   // A broadcast record that dParams[0] already holds (uploaded on this stream) is not sent again, so
   // back-to-back batches with unchanged arguments are kernel launches only.  Otherwise stage through
   // pinned memory; an asynchronous upload may still be reading it, hence the event.
@@ -583,9 +623,53 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
     // scattered frames: stage them one by one into the handle's device buffer
     const size_t stride = (fbytes + 15u) & ~(size_t)15u;
     if (!in->grow_device(in->dFrames, in->dFramesCap, stride * b.n, false)) return false;
-    for (int i = 0; i < b.n; ++i)
-      CUDA_TRY(cudaMemcpyAsync(in->dFrames + (size_t)i * stride, b.framePtrs[i], fbytes,
-                               b.framesOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    // pinned host frames (or device frames): one gather kernel reads them in place; anything else (pageable memory)
+    // goes frame by frame through the copy engine, neighbours in memory merged into one copy
+    bool gathered = false;
+    if (g_gatherMode >= 0 && (g_gatherMode > 0 || b.n >= 8) && stride == fbytes)
+    {
+      if (in->hPtrsFree)
+        CUDA_TRY(cudaEventSynchronize(in->hPtrsFree));
+      else
+        CUDA_TRY(cudaEventCreateWithFlags(&in->hPtrsFree, cudaEventDisableTiming));
+      if (!in->grow_pinned(in->hPtrs, in->hPtrsCap, (size_t)b.n)) return false;
+      if (!in->grow_device(in->dPtrs, in->dPtrsCap, (size_t)b.n, false)) return false;
+      bool all = true;
+      for (int i = 0; all && i < b.n; ++i)
+      {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, b.framePtrs[i]) != cudaSuccess)
+        {
+          cudaGetLastError();
+          all = false;
+        }
+        else if (b.framesOnDevice)
+          all = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr.devicePointer != nullptr;
+        else
+          all = attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+        if (all)
+          all = (((uintptr_t)attr.devicePointer) & 15u) == 0;
+        if (all)
+          in->hPtrs[i] = reinterpret_cast<const uint8_t*>(attr.devicePointer);
+      }
+      if (all)
+      {
+        CUDA_TRY(cudaMemcpyAsync(in->dPtrs, in->hPtrs, sizeof(uint8_t*) * b.n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaEventRecord(in->hPtrsFree, s));
+        CUDA_TRY(launch_gather_frames(in->dPtrs, in->dFrames, (long long)stride, fbytes, b.n, s));
+        gathered = true;
+      }
+    }
+    if (!gathered)
+      for (int i = 0; i < b.n; )
+      {
+        int j = i + 1;
+        while (j < b.n && stride == fbytes && b.framePtrs[j] == b.framePtrs[j - 1] + fbytes)
+          ++j;
+        CUDA_TRY(cudaMemcpyAsync(in->dFrames + (size_t)i * stride, b.framePtrs[i], fbytes * (size_t)(j - i),
+                                 b.framesOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        i = j;
+      }
     dFrames = in->dFrames;
     g.frameStride = (int64_t)stride;
   }
@@ -662,7 +746,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
         const FrameParams& fp = in->paramsScratch[0];
         const bool have = in->lutValid && in->lutStream == s && in->lutFrom == fp.from && in->lutTo == fp.to
                           && in->lutExpected == fp.expected;
-        useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32);
+        useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32) || (b.n >= 32 && lut_set_recurs(in, fp));
         if (useLut && !ensure_lut(in, fp, have, s)) return false;
       }
       if (useLut)
@@ -724,7 +808,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       {
         const bool have = in->lutValid && in->lutStream == s && in->lutFrom == fp0.from && in->lutTo == fp0.to
                           && in->lutExpected == fp0.expected;
-        useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32);
+        useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32) || (b.n >= 32 && lut_set_recurs(in, fp0));
         if (useLut && !ensure_lut(in, fp0, have, s)) return false;
       }
       CUDA_TRY(launch_oo(g, b.n, dFrames, in->dParams, pstride, in->dBitmaps, in->dClusters, in->dEqual, maxLabels, dOut, nullptr, s,
@@ -1405,6 +1489,114 @@ XDAS_Int32 trikb200_processBatch(IVIDTRANSCODE_Handle handle, const TRIKB200_Bat
   return run_batch(in, b) ? IVIDTRANSCODE_EOK : IVIDTRANSCODE_EFAIL;
 }
 
+// frames shard by batch across the GPUs of one box -- one host thread and one stream set per GPU, no
+// collective on the per-pixel path, the results land in the caller's one array.
+XDAS_Int32 trikb200_processBatchMulti(const IVIDTRANSCODE_Handle* handles, XDAS_Int32 numHandles, const TRIKB200_Batch* batch)
+{
+  if (!handles || numHandles < 1 || !batch || batch->size != (XDAS_Int32)sizeof(TRIKB200_Batch))
+  {
+    set_error("bad handle table or TRIKB200_Batch.size");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if (numHandles == 1)
+    return trikb200_processBatch(handles[0], batch);
+  std::vector<Instance*> ins((size_t)numHandles);
+  for (int d = 0; d < numHandles; ++d)
+  {
+    TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(handles[d]);
+    Instance* in = h ? instance_of(h) : nullptr;
+    const Instance* l = ins[0];
+    if (!in || !in->valid
+        || (d > 0 && (in == l || in->kind != l->kind || in->geo.width != l->geo.width || in->geo.height != l->geo.height
+                      || in->geo.lineLength != l->geo.lineLength || in->outWidth != l->outWidth
+                      || in->outHeight != l->outHeight || in->outLineLength != l->outLineLength)))
+    {
+      set_error("processBatchMulti: the handles must be distinct instances of one sensor kind and geometry");
+      return IVIDTRANSCODE_EFAIL;
+    }
+    for (int e = 0; e < d; ++e)
+      if (ins[(size_t)e] == in)
+      {
+        set_error("processBatchMulti: the same handle given twice");
+        return IVIDTRANSCODE_EFAIL;
+      }
+    ins[(size_t)d] = in;
+  }
+  if (batch->framesMem != TRIKB200_MEM_HOST || batch->outArgsMem != TRIKB200_MEM_HOST
+      || (batch->previews && batch->previewsMem != TRIKB200_MEM_HOST) || batch->stream || batch->streamIds
+      || (batch->flags & TRIKB200_BATCH_ASYNC))
+  {
+    set_error("processBatchMulti: host frames, results and previews only; synchronous; no caller stream, no streamIds");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  const int n = batch->numFrames;
+  if (n < 0 || (n > 0 && (!batch->frames || !batch->inArgsAlg || !batch->outArgsAlg)))
+  {
+    set_error("null batch pointers");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  if (n == 0)
+    return IVIDTRANSCODE_EOK;
+  const int kind = ins[0]->kind;
+  if (batch->inArgsStride != 0 && batch->inArgsStride < (XDAS_Int32)in_args_alg_size(kind))
+  {
+    set_error("inArgsStride smaller than the sensor's struct");
+    return IVIDTRANSCODE_EFAIL;
+  }
+  // contiguous frame ranges, the first n % D of them one frame longer
+  std::vector<int> first((size_t)numHandles + 1, 0);
+  for (int d = 0; d < numHandles; ++d)
+    first[(size_t)d + 1] = first[(size_t)d] + n / numHandles + (d < n % numHandles ? 1 : 0);
+  // Carried state (the ov7670 line sensor's lagging band, the object sensor's persisting range) is a function of the
+  // arguments alone: walk it over the whole batch on the host so that every range starts from the state the frame before
+  // it leaves behind -- the results are those of n sequential process() calls on handles[0].
+  const bool carries = kind == KIND_OL || kind == KIND_OO;
+  CarriedState walk = ins[0]->state;
+  if (carries)
+    for (int d = 0; d < numHandles; ++d)
+    {
+      ins[(size_t)d]->state = walk;
+      FrameParams scratch;
+      for (int i = first[(size_t)d]; i < first[(size_t)d + 1]; ++i)
+        prepare_frame_params(kind, ins[0]->geo, reinterpret_cast<const uint8_t*>(batch->inArgsAlg) + (size_t)i * batch->inArgsStride,
+                             walk, scratch);
+    }
+  std::vector<XDAS_Int32> rets((size_t)numHandles, IVIDTRANSCODE_EOK);
+  std::vector<std::string> errors((size_t)numHandles);
+  auto work = [&](int d)
+  {
+    const int lo = first[(size_t)d], cnt = first[(size_t)d + 1] - lo;
+    if (cnt <= 0)
+      return;
+    TRIKB200_Batch sub = *batch;
+    sub.numFrames = cnt;
+    sub.frames = reinterpret_cast<const uint8_t*>(batch->frames) + (int64_t)lo * batch->frameStride;
+    sub.inArgsAlg = reinterpret_cast<const uint8_t*>(batch->inArgsAlg) + (size_t)lo * batch->inArgsStride;
+    sub.outArgsAlg = reinterpret_cast<uint8_t*>(batch->outArgsAlg) + (size_t)lo * batch->outArgsStride;
+    if (batch->seeds) sub.seeds = batch->seeds + lo;
+    if (batch->previews) sub.previews = reinterpret_cast<uint8_t*>(batch->previews) + (int64_t)lo * batch->previewStride;
+    rets[(size_t)d] = trikb200_processBatch(handles[d], &sub);
+    if (rets[(size_t)d] != IVIDTRANSCODE_EOK)
+      errors[(size_t)d] = t_lastError;
+  };
+  std::vector<std::thread> pool;
+  for (int d = 1; d < numHandles; ++d)
+    pool.emplace_back(work, d);
+  work(0);
+  for (auto& th : pool)
+    th.join();
+  if (carries)
+    for (int d = 0; d < numHandles; ++d)
+      ins[(size_t)d]->state = walk;
+  for (int d = 0; d < numHandles; ++d)
+    if (rets[(size_t)d] != IVIDTRANSCODE_EOK)
+    {
+      t_lastError = errors[(size_t)d];
+      return IVIDTRANSCODE_EFAIL;
+    }
+  return IVIDTRANSCODE_EOK;
+}
+
 XDAS_Int32 trikb200_processMixed(const TRIKB200_MixedEntry* entries, XDAS_Int32 numEntries)
 {
   if (numEntries < 0 || (numEntries > 0 && !entries))
@@ -1412,63 +1604,84 @@ XDAS_Int32 trikb200_processMixed(const TRIKB200_MixedEntry* entries, XDAS_Int32 
     set_error("null entries");
     return IVIDTRANSCODE_EFAIL;
   }
-  // group by handle, keeping each handle's entries in order (carried state!)
+  // Group by (sensor kind, device, geometry), not by handle: the reference's model is one codec instance per camera, so a
+  // rig of 1024 cameras is 1024 handles, and all handles of one class go through ONE launch per kernel.  A class borrows
+  // the workspace and stream of its first handle; each frame is judged with (and advances) the carried state of ITS OWN
+  // handle, in entry order, so the results are those of per-handle process() calls.
   struct Group {
-    TrikB200Handle* h;
+    Instance* lead;
     std::vector<const uint8_t*> frames, ins;
     std::vector<uint8_t*> outs;
     std::vector<int64_t> seeds;
+    std::vector<CarriedState*> states;
     BatchView view{};
     Pending pend;
     bool enqueued = false;
   };
   std::vector<Group> groups;
+  Group* last = nullptr;
   for (int i = 0; i < numEntries; ++i)
   {
     const TRIKB200_MixedEntry& e = entries[i];
     TrikB200Handle* h = reinterpret_cast<TrikB200Handle*>(e.handle);
-    if (!h || !instance_of(h) || !e.frame || !e.inArgsAlg || !e.outArgsAlg)
+    Instance* in = h ? instance_of(h) : nullptr;
+    if (!in || !e.frame || !e.inArgsAlg || !e.outArgsAlg)
     {
       set_error("null pointer in a mixed entry");
       return IVIDTRANSCODE_EFAIL;
     }
-    Group* gptr = nullptr;
-    for (Group& g : groups)
-      if (g.h == h) { gptr = &g; break; }
+    if (!in->valid || in->geo.width <= 0 || in->geo.height <= 0)
+    {
+      set_error("algorithm not set up for a non-empty image");
+      return IVIDTRANSCODE_EFAIL;
+    }
+    auto same_class = [in](const Group& g) {
+      const Instance* l = g.lead;
+      return l == in || (l->kind == in->kind && l->device == in->device && l->geo.width == in->geo.width
+                         && l->geo.height == in->geo.height && l->geo.lineLength == in->geo.lineLength);
+    };
+    Group* gptr = (last && same_class(*last)) ? last : nullptr;
+    if (!gptr)
+      for (Group& g : groups)
+        if (same_class(g)) { gptr = &g; break; }
     if (!gptr)
     {
       groups.emplace_back();
       gptr = &groups.back();
-      gptr->h = h;
+      gptr->lead = in;
     }
+    last = nullptr;                       // (groups may have been reallocated)
     gptr->frames.push_back(reinterpret_cast<const uint8_t*>(e.frame));
     gptr->ins.push_back(reinterpret_cast<const uint8_t*>(e.inArgsAlg));
     gptr->outs.push_back(reinterpret_cast<uint8_t*>(e.outArgsAlg));
     gptr->seeds.push_back(e.seed);
+    gptr->states.push_back(&in->state);
+    last = gptr;
   }
-  // enqueue every handle's work on its own stream, then finish them all: the handles overlap on the GPU
+  // enqueue every class on its lead handle's stream, then finish them all: the classes overlap on the GPU
   bool ok = true;
   for (Group& g : groups)
   {
     BatchView& b = g.view;
     b.n = (int)g.frames.size();
     b.framePtrs = g.frames.data(); b.inPtrs = g.ins.data(); b.outPtrs = g.outs.data();
+    b.statePtrs = g.states.data();
     b.framesOnDevice = false; b.outOnDevice = false;
-    b.inStride = (int)in_args_alg_size(g.h->kind); b.outStride = (int)out_args_alg_size(g.h->kind);
+    b.inStride = (int)in_args_alg_size(g.lead->kind); b.outStride = (int)out_args_alg_size(g.lead->kind);
     b.seeds = g.seeds.data(); b.seedsBroadcast = false;
     b.stream = nullptr; b.async = false;
-    if ((instance_of(g.h)->geo.lineLength & 15) != 0)
+    if ((g.lead->geo.lineLength & 15) != 0)
     {
       set_error("inputLineLength must be a multiple of 16");
       ok = false;
       break;
     }
-    g.enqueued = enqueue_batch(instance_of(g.h), b, g.pend);
+    g.enqueued = enqueue_batch(g.lead, b, g.pend);
     if (!g.enqueued) { ok = false; break; }
   }
   for (Group& g : groups)
     if (g.enqueued && g.pend.needsFinish)
-      ok = finish_batch(instance_of(g.h), g.view, g.pend) && ok;
+      ok = finish_batch(g.lead, g.view, g.pend) && ok;
   return ok ? IVIDTRANSCODE_EOK : IVIDTRANSCODE_EFAIL;
 }
 
@@ -1522,6 +1735,7 @@ void trikb200_setBlockThreads(XDAS_Int32 threads) { set_target_threads(threads);
 void trikb200_setOverlapLaunch(XDAS_Int32 on) { set_overlap_launch(on); }
 void trikb200_setLutMode(XDAS_Int32 mode) { g_lutMode = mode; }
 void trikb200_setMxnTableMode(XDAS_Int32 mode) { g_mxnTableMode = mode; }
+void trikb200_setGatherMode(XDAS_Int32 mode) { g_gatherMode = mode; }
 void trikb200_setLutSkew(XDAS_Int32 on) { set_lut_skew(on); }
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant) { set_edge_variant(variant); }
 void trikb200_setMxnTableThreads(XDAS_Int32 threads) { set_om_table_threads(threads); }

@@ -142,6 +142,10 @@ void set_lut_skew(int on);
 // RGB565 -> YUV422P ingest front end (trik_kernels_ingest.cu)
 cudaError_t launch_ingest_rgb565(const uint8_t* src, long long srcStride, int srcLine, uint8_t* dst, long long dstStride,
                                  int dstLine, int width, int height, int numFrames, int bgr, int smCount, cudaStream_t stream);
+// scattered pinned host frames -> one device batch buffer (trik_kernels_ingest.cu); dSrcPtrs is a device array of the
+// frames' device-visible addresses
+cudaError_t launch_gather_frames(const uint8_t* const* dSrcPtrs, uint8_t* dst, long long dstStride, size_t frameBytes,
+                                 int numFrames, cudaStream_t stream);
 // ov7670/edge_line_sensor (trik_kernels_edge.cu): out record i at out + i * outStride bytes
 cudaError_t launch_edge_line(const uint8_t* frames, long long frameStride, int lineLength, int width, int height,
                              int numFrames, TargetOut* out, int outStride, cudaStream_t stream);

@@ -95,4 +95,53 @@ cudaError_t launch_ingest_rgb565(const uint8_t* src, long long srcStride, int sr
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Scattered pinned host frames -> the handle's device batch buffer, in ONE launch.
+// trikb200_processMixed hands over one pointer per frame (the reference's model is one codec instance per camera, so a time
+// step of 1024 streams is 1024 separate buffers).  One cudaMemcpyAsync per frame costs about 2 us of host time each, more
+// than the 2.8 us the 153.6 KB take on the PCIe link; this kernel reads the pinned buffers in place instead (the host
+// pointers are device pointers under unified addressing) with 64 bytes per thread in flight, and writes the frames at
+// i * dstStride as the sensor kernels expect them.  No arithmetic: bound by the PCIe read bandwidth.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_frames_kernel(const uint8_t* const* __restrict__ srcPtrs, uint8_t* __restrict__ dst, const long long dstStride,
+                     const uint32_t chunks /* 16-byte units per frame */, const int numFrames)
+{
+  for (int frame = blockIdx.y; frame < numFrames; frame += gridDim.y)
+  {
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(srcPtrs[frame]);
+    uint4* __restrict__ out = reinterpret_cast<uint4*>(dst + (long long)frame * dstStride);
+    const uint32_t step = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3u * step < chunks; i += 4u * step)
+    {
+      const uint4 a = ld_stream(reinterpret_cast<const uint8_t*>(src + i));
+      const uint4 b = ld_stream(reinterpret_cast<const uint8_t*>(src + i + step));
+      const uint4 c = ld_stream(reinterpret_cast<const uint8_t*>(src + i + 2u * step));
+      const uint4 d = ld_stream(reinterpret_cast<const uint8_t*>(src + i + 3u * step));
+      out[i] = a; out[i + step] = b; out[i + 2u * step] = c; out[i + 3u * step] = d;
+    }
+    for (; i < chunks; i += step)
+      out[i] = ld_stream(reinterpret_cast<const uint8_t*>(src + i));
+  }
+}
+
+cudaError_t launch_gather_frames(const uint8_t* const* dSrcPtrs, uint8_t* dst, long long dstStride, size_t frameBytes,
+                                 int numFrames, cudaStream_t stream)
+{
+  if (numFrames <= 0)
+    return cudaSuccess;
+  if ((frameBytes & 15) || (dstStride & 15) || frameBytes / 16 >= (1ull << 30))
+    return cudaErrorInvalidValue;
+  const uint32_t chunks = (uint32_t)(frameBytes / 16);
+  // about 4 KB per CTA pass: enough CTAs in flight to cover the link latency even for a handful of frames
+  unsigned perFrame = (chunks + 1023u) / 1024u;
+  if (perFrame < 1u) perFrame = 1u;
+  if (perFrame > 8u) perFrame = 8u;
+  const dim3 grid(perFrame, (unsigned)(numFrames < 65535 ? numFrames : 65535));
+  gather_frames_kernel<<<grid, 256, 0, stream>>>(dSrcPtrs, dst, dstStride, chunks, numFrames);
+  ++g_launches_ingest;
+  return cudaGetLastError();
+}
+
 } // namespace trikb200

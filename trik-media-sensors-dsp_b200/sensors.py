@@ -39,6 +39,8 @@ def lib():
         l.trikb200_delete.argtypes = [C.c_void_p]
         l.trikb200_processBatch.argtypes = [C.c_void_p, C.POINTER(xdm.Batch)]
         l.trikb200_processBatch.restype = C.c_int32
+        l.trikb200_processBatchMulti.argtypes = [C.c_void_p, C.c_int32, C.POINTER(xdm.Batch)]
+        l.trikb200_processBatchMulti.restype = C.c_int32
         l.trikb200_processMixed.argtypes = [C.c_void_p, C.c_int32]
         l.trikb200_processMixed.restype = C.c_int32
         l.trikb200_synchronize.argtypes = [C.c_void_p]
@@ -51,6 +53,7 @@ def lib():
         l.trikb200_setOverlapLaunch.argtypes = [C.c_int32]
         l.trikb200_setLutMode.argtypes = [C.c_int32]
         l.trikb200_setMxnTableMode.argtypes = [C.c_int32]
+        l.trikb200_setGatherMode.argtypes = [C.c_int32]
         l.trikb200_setLutSkew.argtypes = [C.c_int32]
         l.trikb200_setEdgeLineVariant.argtypes = [C.c_int32]
         l.trikb200_setMxnTableThreads.argtypes = [C.c_int32]
@@ -265,8 +268,9 @@ class Codec:
 
     def process_batch(self, frames, in_algs, out_algs=None, seeds=None, frames_device=False, frame_stride=None,
                       num_frames=None, out_device_ptr=None, stream=None, flags=0, stream_ids=None, num_streams=0,
-                      previews=None, previews_device_ptr=None, preview_stride=None):
-        """n frames == n sequential process() calls.
+                      previews=None, previews_device_ptr=None, preview_stride=None, multi=None):
+        """n frames == n sequential process() calls.  multi: a list of codecs of this kind and geometry (self first), one
+        per GPU: the batch is cut into contiguous ranges, one per codec (trikb200_processBatchMulti).
 
         frames: (n, frame_bytes) uint8 numpy array, or a raw device pointer (int) with
         frames_device=True, frame_stride and num_frames.  in_algs: one InArgsAlg (broadcast) or a
@@ -310,7 +314,11 @@ class Codec:
         if stream_ids is not None:
             keep_ids = (C.c_int32 * n)(*[int(x) for x in stream_ids])
             b.streamIds, b.numStreams = C.addressof(keep_ids), int(num_streams)
-        ret = self.lib.trikb200_processBatch(self.handle, C.byref(b))
+        if multi is not None:
+            tab = (C.c_void_p * len(multi))(*[c.handle for c in multi])
+            ret = self.lib.trikb200_processBatchMulti(tab, len(multi), C.byref(b))
+        else:
+            ret = self.lib.trikb200_processBatch(self.handle, C.byref(b))
         return ret, out_algs
 
     def synchronize(self):
