@@ -18,7 +18,7 @@ def _case(kind, n):
     if kind == "oo":
         arr = (xdm.ObjInArgsAlg * n)()
         for i in range(n):                       # the range is set at frames 0 and 7 only; everything else lives on the carried one
-            arr[i] = xdm.ObjInArgsAlg(1, 0, 20, 80, 20, 50, 30, 0) if i == 0 else \\
+            arr[i] = xdm.ObjInArgsAlg(1, 0, 20, 80, 20, 50, 30, 0) if i == 0 else \
                 xdm.ObjInArgsAlg(1, 0, 30, 70, 25, 60, 30, 0) if i == 7 else xdm.ObjInArgsAlg(0, 0, 0, 0, 0, 0, 0, 0)
         return "blobs", arr, 24
     if kind == "om":
