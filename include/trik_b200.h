@@ -351,6 +351,9 @@ void trikb200_setGatherMode(XDAS_Int32 mode);
  * instead of 256 bytes apart): no bank conflicts when the chroma of neighbouring pixels differs by a little (camera noise),
  * for one more instruction per pixel pair (+60..75 % on such frames, -4 % on frames with noise-free chroma); 0 = plain rows */
 void trikb200_setLutSkew(XDAS_Int32 on);
+/* tuning knob: work items of the webcam object sensor's table kernel: 0 (default) = whole frames, or 2 / 4 / 8 bands of rows
+ * per frame when whole frames would leave the last round of the persistent groups mostly idle; 1 / 2 / 4 / 8 = fixed */
+void trikb200_setLutParts(XDAS_Int32 parts);
 /* tuning knob: edge-line kernel, 0 = packed four-pixels-per-thread form (default, needs 4-byte aligned rows), 1 = one thread
  * per column (first version) */
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant);

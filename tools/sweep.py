@@ -34,6 +34,7 @@ def main():
     sensors.lib().trikb200_setMxnTableMode(int(os.environ.get("OMTAB", "0")))   # -1: arithmetic mxn kernel only
     sensors.lib().trikb200_setMxnTableThreads(int(os.environ.get("OMTHREADS", "0")))
     sensors.lib().trikb200_setLutSkew(int(os.environ.get("SKEW", "1")))
+    sensors.lib().trikb200_setLutParts(int(os.environ.get("LUTPARTS", "0")))        # bands per frame of the WO table kernel
     sensors.lib().trikb200_setOverlapLaunch(int(os.environ.get("OVERLAP", "1")))   # 0: no programmatic dependent launches
     peak = 6541.1
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -77,9 +78,13 @@ def main():
             else:
                 ia = xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 40, 0)
 
+            # PREVIEW=1: with the RGB565X preview (1:1, device memory) as process() always produces it
+            pv = torch.empty((n, fbytes), dtype=torch.uint8, device=dev) if os.environ.get("PREVIEW") == "1" else None
+            pkw = {"previews_device_ptr": pv.data_ptr(), "preview_stride": fbytes} if pv is not None else {}
+
             def step():
                 ret, _ = codec.process_batch(d_frames.data_ptr(), ia, frames_device=True, frame_stride=fbytes, num_frames=n,
-                                             out_device_ptr=d_out.data_ptr(), stream=sptr, flags=xdm.BATCH_ASYNC)
+                                             out_device_ptr=d_out.data_ptr(), stream=sptr, flags=xdm.BATCH_ASYNC, **pkw)
                 assert ret == 0, sensors.last_error()
 
             for _ in range(3):
@@ -96,7 +101,7 @@ def main():
             gbs = n * w * h * 2 / (ms / 1e3) / 1e9
             print(json.dumps({"sensor": kind, "width": w, "height": h, "batch": n, "family": fam, "ms_per_batch": ms,
                               "frames_per_sec": n / (ms / 1e3), "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / peak,
-                              "launches_per_batch": (launch_count() - l0) / args.steps}), flush=True)
+                              "launches_per_batch": (launch_count() - l0) / args.steps, "preview": pv is not None}), flush=True)
             codec.close()
             del d_frames, d_out
 

@@ -750,8 +750,11 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
         if (useLut && !ensure_lut(in, fp, have, s)) return false;
       }
       if (useLut)
+      {
+        if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
         CUDA_TRY(launch_wo_lut(g, b.n, dFrames, in->dParams, in->dLutTable, in->dLutMasks,
-                               reinterpret_cast<TargetOut*>(dOut), in->smCount, s));
+                               reinterpret_cast<TargetOut*>(dOut), in->smCount, s, in->dAcc));
+      }
       else
       {
         if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
@@ -1737,6 +1740,7 @@ void trikb200_setLutMode(XDAS_Int32 mode) { g_lutMode = mode; }
 void trikb200_setMxnTableMode(XDAS_Int32 mode) { g_mxnTableMode = mode; }
 void trikb200_setGatherMode(XDAS_Int32 mode) { g_gatherMode = mode; }
 void trikb200_setLutSkew(XDAS_Int32 on) { set_lut_skew(on); }
+void trikb200_setLutParts(XDAS_Int32 parts) { set_lut_parts(parts); }
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant) { set_edge_variant(variant); }
 void trikb200_setMxnTableThreads(XDAS_Int32 threads) { set_om_table_threads(threads); }
 void trikb200_setZeroCopyBytes(XDAS_Int32 bytes) { g_zeroCopyBytes = bytes; }

@@ -117,7 +117,9 @@ cudaError_t launch_oo_bitmap_lut(const Geometry& g, int numFrames, const uint8_t
 cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, const uint8_t* table, const uint32_t* masks,
                              unsigned long long* stats, cudaStream_t stream);
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
-                          const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream);
+                          const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream,
+                          SumAcc* acc = nullptr);
+void set_lut_parts(int parts);
 cudaError_t launch_line_bulk(bool planar, const Geometry& g, long long grid, int threads, const uint8_t* frames,
                              const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,
                              int slabs, int rowsPerSlab, int cpr, int rpi, int stages, bool overlap, cudaStream_t stream);

@@ -34,6 +34,8 @@ namespace trikb200 {
 std::atomic<long long> g_launches_lut{0};
 static int g_lutSkew = 1;
 void set_lut_skew(int on) { g_lutSkew = on; }
+static int g_lutParts = 0;                    // bands per frame of the WO table kernel: 0 = chosen per launch, 1 / 2 / 4 / 8 = fixed
+void set_lut_parts(int parts) { g_lutParts = parts; }
 
 // (lo, nhi = 255 - hi) codes with lo > hi: no luma satisfies lo <= Y <= hi, so the interval test fails by itself
 constexpr uint32_t LUT_NEVER_LO = 255u, LUT_NEVER_NHI = 255u;        // hi = 0
@@ -157,7 +159,8 @@ template <int STAGES, bool SKEW>
 __global__ void __launch_bounds__(1024, 1)
 wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
               const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
-              const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi)
+              const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi,
+              const int parts, const int rowsPerPart, SumAcc* __restrict__ acc)
 {
   constexpr uint32_t STRIDE = SKEW ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN;
   extern __shared__ __align__(16) uint8_t s_raw[];
@@ -182,7 +185,6 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   const int cc = tg % cpr;
   const int rr = tg / cpr;
   const int warpInGroup = tg >> 5, lane = tg & 31, gwarps = gthreads >> 5;
-  const int itersAll = rr < g.height ? (g.height - rr + rpi - 1) / rpi : 0;
   const size_t rowStep = (size_t)rpi * g.lineLength;
   const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(s_table);
   const uint32_t stageBytes = (uint32_t)(groups * gthreads) * 16u;
@@ -191,9 +193,16 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   const FrameParams p = params[0];
   const uint32_t W = (uint32_t)g.width, H = (uint32_t)g.height;
 
-  for (int frame = blockIdx.x * groups + group; frame < numFrames; frame += gridDim.x * groups)
+  // A work item is one frame, or -- when whole frames would leave the last round of the persistent groups mostly empty
+  // (1024 frames on 888 groups: two rounds for 1.15 rounds of work) -- one of `parts` bands of rowsPerPart rows; the bands of
+  // a frame meet in its SumAcc record (zero between launches, as the sum kernels keep it) and the last one finalises.
+  for (int item = blockIdx.x * groups + group; item < numFrames * parts; item += gridDim.x * groups)
   {
-    const uint8_t* fillPtr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)rr * g.lineLength;
+    const int frame = parts == 1 ? item : item / parts;
+    const int row0 = parts == 1 ? 0 : (item - frame * parts) * rowsPerPart;
+    const int rowsHere = min(rowsPerPart, g.height - row0);
+    const int itersAll = rr < rowsHere ? (rowsHere - rr + rpi - 1) / rpi : 0;
+    const uint8_t* fillPtr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)(row0 + rr) * g.lineLength;
     uint32_t passes = 0u, inIdx = 0u, syPass = 0u;       // 32-bit totals of this thread
     int fillIt = 0;
 #pragma unroll
@@ -266,7 +275,7 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
       const uint32_t segPasses = (S & 0xFFFFu) + (S >> 16);
       passes += segPasses;
       inIdx  += 2u * ((A & 0xFFFFu) + (A >> 16)) + (S >> 16);
-      syPass += segPasses * (uint32_t)(rr + seg0 * rpi) + (uint32_t)rpi * ((SI & 0xFFFFu) + (SI >> 16));
+      syPass += segPasses * (uint32_t)(row0 + rr + seg0 * rpi) + (uint32_t)rpi * ((SI & 0xFFFFu) + (SI >> 16));
       S = 0u; A = 0u; SI = 0u;
     }
     uint32_t sxPass = passes * ((uint32_t)cc * 8u) + inIdx;
@@ -290,8 +299,25 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
       a = __reduce_add_sync(0xFFFFFFFFu, a);
       b = __reduce_add_sync(0xFFFFFFFFu, b);
       c = __reduce_add_sync(0xFFFFFFFFu, c);
-      if (lane == 0)      // finalize_sum works from the FAILING pixels' sums (all arithmetic modulo 2^32, as there)
-        finalize_sum<KIND_WO>(g, p, W * H - a, H * (W * (W - 1u) / 2u) - b, W * (H * (H - 1u) / 2u) - c, 0u, out + frame, out);
+      if (lane == 0)
+      {
+        bool last = true;
+        if (parts > 1)
+        {
+          SumAcc* const fa = acc + frame;
+          atomicAdd(&fa->fails, a); atomicAdd(&fa->sxFail, b); atomicAdd(&fa->syFail, c);      // (sums of the PASSING pixels here)
+          __threadfence();
+          last = atomicAdd(&fa->done, 1u) == (uint32_t)(parts - 1);
+          if (last)
+          {
+            __threadfence();
+            a = atomicExch(&fa->fails, 0u); b = atomicExch(&fa->sxFail, 0u); c = atomicExch(&fa->syFail, 0u);
+            fa->done = 0u;
+          }
+        }
+        if (last)         // finalize_sum works from the FAILING pixels' sums (all arithmetic modulo 2^32, as there)
+          finalize_sum<KIND_WO>(g, p, W * H - a, H * (W * (W - 1u) / 2u) - b, W * (H * (H - 1u) / 2u) - c, 0u, out + frame, out);
+      }
     }
     group_barrier(1 + group, gthreads);                  // myRed is reused by the next frame
   }
@@ -453,7 +479,8 @@ cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, cons
 }
 
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
-                          const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream)
+                          const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream,
+                          SumAcc* acc)
 {
   if (numFrames <= 0)
     return cudaSuccess;
@@ -473,7 +500,28 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
   if (smem_for(groups) > 227 * 1024)
     return cudaErrorInvalidValue;
   const int threads = ((groups * gthreads + 31) / 32) * 32;
-  int grid = (numFrames + groups - 1) / groups;
+  // bands per frame: the fewest of 1, 2, 4, 8 that fill the last round of the persistent groups to 90 % (a band is at least
+  // 2 * STAGES row iterations), else the best of them; needs the accumulator records
+  int parts = 1;
+  if (acc && g_lutParts != 1)
+  {
+    const long long slots = (long long)smCount * groups;
+    double best = 0.0;
+    for (int cand = 1; cand <= 8; cand *= 2)
+    {
+      if (cand > 1 && g.height / cand < rpi * 2 * STAGES)
+        break;
+      if (g_lutParts > 1 && cand != g_lutParts)
+        continue;
+      const long long items = (long long)numFrames * cand;
+      const double eff = items <= slots ? 1.0 : (double)items / slots / (double)((items + slots - 1) / slots);
+      if (eff > best + 1e-9) { best = eff; parts = cand; }
+      if (eff >= 0.9)
+        break;
+    }
+  }
+  const int rowsPerPart = (((g.height + parts - 1) / parts + rpi - 1) / rpi) * rpi;     // whole row iterations per band
+  int grid = (int)(((long long)numFrames * parts + groups - 1) / groups);
   if (grid > smCount) grid = smCount;
   const size_t smem = smem_for(groups);
   cudaError_t e = skew ? cudaFuncSetAttribute(wo_lut_kernel<STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -481,9 +529,9 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
   if (e != cudaSuccess)
     return e;
   if (skew)
-    wo_lut_kernel<STAGES, true><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi);
+    wo_lut_kernel<STAGES, true><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc);
   else
-    wo_lut_kernel<STAGES, false><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi);
+    wo_lut_kernel<STAGES, false><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc);
   ++g_launches_lut;
   return cudaGetLastError();
 }

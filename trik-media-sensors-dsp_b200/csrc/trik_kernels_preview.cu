@@ -121,8 +121,136 @@ preview_base_kernel(const Geometry g, const uint8_t* __restrict__ frames, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// 1:1 previews (outputWidth x outputHeight == the frame: the reference's default for the object sensors) -- both index maps
+// are the identity, so the gather is a plain stream: 8 pixels per thread, one 16-byte load (two 8-byte loads for the planar
+// sensors) and one 16-byte store, the colour conversion on pixel PAIRS in 16-bit lanes as in the sum kernels.  The generic
+// kernel above (one scalar load and a 64-bit division per destination pair) stays for every other geometry.
+// colFirst..colLast: the source columns pass 2 visits at all (5..W-5 for the ov7670 line sensor, everything else 0..W-1).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rgb565x_pair(uint32_t r2, uint32_t g2, uint32_t b2)       // lanes 0x00CC00CC
+{
+  return ((r2 >> 3) & 0x001F001Fu) | ((g2 << 3) & 0x07E007E0u) | ((b2 << 8) & 0xF800F800u);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+                        const int paramStride, const uint16_t* __restrict__ bitmaps, const int outLine,
+                        uint8_t* __restrict__ previews, const long long previewStride, const int numFrames,
+                        const uint32_t cprMagic, const int colFirst, const int colLast)
+{
+  constexpr bool PLANAR = (KIND == KIND_OO || KIND == KIND_OL || KIND == KIND_OM);
+  __shared__ uint16_t s_lut43[256];
+  __shared__ uint16_t s_lut255[256];
+  __shared__ HueLutEntry s_lutHue[KIND == KIND_WO ? 256 : 1];
+  if (KIND == KIND_WO)
+  {
+    fill_div_luts(s_lut43, s_lut255);
+    fill_hue_lut(s_lutHue);
+    __syncthreads();
+  }
+  const int cpr = g.width >> 3;
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= (uint32_t)cpr * (uint32_t)g.height)
+    return;
+  const int row = (int)__umulhi(item, cprMagic), c = (int)item - row * cpr;
+  const int col0 = c * 8;
+  for (int frame = blockIdx.y; frame < numFrames; frame += gridDim.y)
+  {
+    const uint8_t* fr = frames + (size_t)frame * g.frameStride;
+    uint32_t yy[4], cw[4];
+    if (!PLANAR)
+    {
+      const uint4 in = ld_stream(fr + (size_t)row * g.lineLength + (size_t)c * 16);
+      cw[0] = in.x; cw[1] = in.y; cw[2] = in.z; cw[3] = in.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) yy[j] = cw[j] & 0x00FF00FFu;
+    }
+    else
+    {
+      const uint2 l = *reinterpret_cast<const uint2*>(fr + (size_t)row * g.lineLength + (size_t)c * 8);
+      const uint2 ch = *reinterpret_cast<const uint2*>(fr + (size_t)(g.height + row) * g.lineLength + (size_t)c * 8);
+      yy[0] = __byte_perm(l.x, 0u, 0x4140); yy[1] = __byte_perm(l.x, 0u, 0x4342);
+      yy[2] = __byte_perm(l.y, 0u, 0x4140); yy[3] = __byte_perm(l.y, 0u, 0x4342);
+      cw[0] = ch.x; cw[1] = ch.x; cw[2] = ch.y; cw[3] = ch.y;
+    }
+    uint32_t from = 0, to = 0, expected = 0;
+    if (KIND == KIND_WO || KIND == KIND_WL || KIND == KIND_OL)
+    {
+      const FrameParams& p = params[(size_t)frame * paramStride];
+      from = p.from; to = p.to; expected = p.expected;
+    }
+    uint32_t on0 = 0, on1 = 0;                                   // OO: the two metapixels under these 8 pixels
+    if (KIND == KIND_OO)
+    {
+      const uint32_t two = *reinterpret_cast<const uint32_t*>(bitmaps + ((size_t)frame * (g.height >> 2) + (size_t)(row >> 2)) * (g.width >> 2)
+                                                              + (size_t)(col0 >> 2));
+      on0 = __popc(two & 0xFFFFu) > 2 ? 0xFFFFFFFFu : 0u;
+      on1 = __popc(two >> 16) > 2 ? 0xFFFFFFFFu : 0u;
+    }
+    // line sensors: V = max(R,G,B) inside vFrom..vTo, tested on the clamped keys (channel = bits 6..13 of a lane):
+    // key - keyLo <= span (mod 2^16); an empty range never passes
+    uint32_t keyLo2 = 0x7FFF7FFFu, span2 = 0u;
+    if (KIND == KIND_WL || KIND == KIND_OL)
+    {
+      const uint32_t vf = (from >> 16) & 0xFFu, vt = (to >> 16) & 0xFFu;
+      if (vf <= vt)
+      {
+        keyLo2 = (0x8000u + (vf << 6)) * 0x10001u;
+        span2 = (((vt - vf) << 6) + 63u) * 0x10001u;
+      }
+    }
+    HsvBounds bd{};
+    if (KIND == KIND_WO)
+      bd = make_bounds(from, to);
+    uint32_t px[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+      const ChromaCoef coef = !PLANAR ? coef_yuyv() : ((j & 1) ? coef_planar1() : coef_planar0());
+      uint32_t kr, kg, kb;
+      rgb_keys(yy[j], cw[j], coef, kr, kg, kb);
+      // clamped keys, lanes 0x8000 + (channel << 6) + 6 low bits; the RGB565X fields are cut straight out of them
+      // (R bits 9..13 -> 0..4, G bits 8..13 -> 5..10, B bits 9..13 -> 11..15), the shifts on the multiplier pipe
+      const uint32_t cr = __vminu2(__vmaxu2(kr, 0x80008000u), 0xBFFFBFFFu);
+      const uint32_t cg = __vminu2(__vmaxu2(kg, 0x80008000u), 0xBFFFBFFFu);
+      const uint32_t cb = __vminu2(__vmaxu2(kb, 0x80008000u), 0xBFFFBFFFu);
+      const uint32_t rgb = (__umulhi(cr, 1u << 23) & 0x001F001Fu) | (__umulhi(cg, 1u << 29) & 0x07E007E0u) | ((cb * 4u) & 0xF800F800u);
+      uint32_t keep = 0xFFFFFFFFu;                               // 0xFFFF in the lanes that keep their own colour
+      if (KIND == KIND_WO)
+      {
+        // the pair-wise threshold of the sum kernel (V, then S, then hue, each with a warp-wide early out)
+        const uint32_t det = detect_pair_bits(yy[j], cw[j], coef, s_lutHue, s_lut255, bd, expected);
+        keep = ~(((det & 1u) * 0x0000FFFFu) | ((det >> 1) * 0xFFFF0000u));
+      }
+      else if (KIND == KIND_WL || KIND == KIND_OL)
+      {
+        const uint32_t d = __vsub2(__vmaxu2(cr, __vmaxu2(cg, cb)), keyLo2);
+        const uint32_t over = __vmaxu2(d, span2) - span2;        // lane 0 <=> inside the range
+        keep = __vminu2(over, 0x00010001u) * 0xFFFFu;
+      }
+      else if (KIND == KIND_OO)
+        keep = j < 2 ? ~on0 : ~on1;
+      uint32_t p2 = (rgb & keep) | (0xFFE0FFE0u & ~keep);        // detected: cyan 0x00ffff -> 0xFFE0
+      if (KIND == KIND_OL)
+      {
+        const int cA = col0 + 2 * j;
+        if (cA < colFirst || cA > colLast) p2 &= 0xFFFF0000u;
+        if (cA + 1 < colFirst || cA + 1 > colLast) p2 &= 0x0000FFFFu;
+      }
+      px[j] = p2;
+    }
+    *reinterpret_cast<uint4*>(previews + (size_t)frame * previewStride + (size_t)row * outLine + (size_t)c * 16)
+        = make_uint4(px[0], px[1], px[2], px[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // overlays
 // ---------------------------------------------------------------------------------------------
+// One CTA of OVERLAY_THREADS threads per frame: primitives in reference order (a block barrier where a later primitive may
+// overwrite an earlier one of another colour), the pixels of one primitive spread over the threads.
+constexpr int OVERLAY_THREADS = 128;
 struct Canvas {
   uint8_t* img;
   int W, H, outLine;
@@ -132,18 +260,18 @@ struct Canvas {
   {
     col = col < 0 ? 0 : (col > W - 1 ? W - 1 : col);
     row = row < 0 ? 0 : (row > H - 1 ? H - 1 : row);
-    *reinterpret_cast<uint16_t*>(img + (size_t)hi2ho[row] * outLine + (size_t)wi2wo[col] * 2u) = rgb565x(rgb);
+    *reinterpret_cast<uint16_t*>(img + (size_t)__ldg(hi2ho + row) * outLine + (size_t)__ldg(wi2wo + col) * 2u) = rgb565x(rgb);
   }
 };
 
 // vertical / horizontal "target" lines of +-100 pixels (WO :136-168), one colour: lanes share the work
 __device__ void centre_line(const Canvas& c, int lane, int col, int row, uint32_t rgb)
 {
-  for (int adj = lane; adj < 100; adj += 32) { c.put(col, row - adj, rgb); c.put(col, row + adj, rgb); }
+  for (int adj = lane; adj < 100; adj += OVERLAY_THREADS) { c.put(col, row - adj, rgb); c.put(col, row + adj, rgb); }
 }
 __device__ void horizontal_centre_line(const Canvas& c, int lane, int col, int row, uint32_t rgb)
 {
-  for (int adj = lane; adj < 100; adj += 32) { c.put(col - adj, row, rgb); c.put(col + adj, row, rgb); }
+  for (int adj = lane; adj < 100; adj += OVERLAY_THREADS) { c.put(col - adj, row, rgb); c.put(col + adj, row, rgb); }
 }
 // Bresenham circle, sequential (WO :91-134)
 __device__ void circle(const Canvas& c, int col, int row, int radius, uint32_t rgb)
@@ -160,7 +288,7 @@ __device__ void circle(const Canvas& c, int col, int row, int radius, uint32_t r
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(OVERLAY_THREADS)
 preview_overlay_kernel(const Geometry g, const FrameParams* __restrict__ params, const int paramStride,
                        const DrawInfo* __restrict__ draw, const int32_t* __restrict__ omColours, const PreviewGeom pg,
                        uint8_t* __restrict__ previews, const long long previewStride)
@@ -176,7 +304,7 @@ preview_overlay_kernel(const Geometry g, const FrameParams* __restrict__ params,
     centre_line(c, lane, hW + step, hH, 0xFF00FFu);     centre_line(c, lane, hW + 2 * step, hH, 0xFF00FFu);
     horizontal_centre_line(c, lane, hW, hH - 2 * step, 0xFF00FFu); horizontal_centre_line(c, lane, hW, hH - step, 0xFF00FFu);
     horizontal_centre_line(c, lane, hW, hH + step, 0xFF00FFu);     horizontal_centre_line(c, lane, hW, hH + 2 * step, 0xFF00FFu);
-    __syncwarp();
+    __syncthreads();
     const DrawInfo d = draw[frame];
     if (KIND == KIND_WO)
     {
@@ -195,24 +323,24 @@ preview_overlay_kernel(const Geometry g, const FrameParams* __restrict__ params,
   else if (KIND == KIND_WL || KIND == KIND_OL)
   {
     // drawRgbThinLine: full-height verticals at hW -+ 40, -+ 80 (WL :384-387); drawY = 0
-    for (int adj = lane; adj < H; adj += 32)
+    for (int adj = lane; adj < H; adj += OVERLAY_THREADS)
     {
       c.put(hW - 40, adj, 0xFF00FFu); c.put(hW + 40, adj, 0xFF00FFu);
       c.put(hW - 80, adj, 0xFF00FFu); c.put(hW + 80, adj, 0xFF00FFu);
     }
-    __syncwarp();
+    __syncthreads();
     if (KIND == KIND_OL)
     {
-      for (int adj = lane; adj < W; adj += 32)                                  // drawRgbHorizontalLine (OL :454-455)
+      for (int adj = lane; adj < W; adj += OVERLAY_THREADS)                                  // drawRgbHorizontalLine (OL :454-455)
       {
         c.put(adj, hH, 0xFF0000u);
         c.put(adj, hH + 80, 0xFF0000u);
       }
-      __syncwarp();
+      __syncthreads();
     }
     const DrawInfo d = draw[frame];
     if (d.v[0])                                                                 // points > 10: 3-wide red line (WL :410)
-      for (int adj = lane; adj < H; adj += 32)
+      for (int adj = lane; adj < H; adj += OVERLAY_THREADS)
       {
         c.put(d.v[1] - 1, adj, 0xFF0000u); c.put(d.v[1], adj, 0xFF0000u); c.put(d.v[1] + 1, adj, 0xFF0000u);
       }
@@ -231,9 +359,9 @@ preview_overlay_kernel(const Geometry g, const FrameParams* __restrict__ params,
       {
         const uint32_t rgb = (uint32_t)colours[i * N + j];
         const int r0 = (uint16_t)(i * hs), c0 = (uint16_t)(j * ws);
-        for (int k = lane; k < 400; k += 32)
+        for (int k = lane; k < 400; k += OVERLAY_THREADS)
           c.put(c0 + k % 20, r0 + k / 20, rgb);
-        __syncwarp();
+        __syncthreads();
       }
   }
 }
@@ -252,9 +380,37 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
   if (gy > 65535u)
     return cudaErrorInvalidValue;
   dim3 grid((unsigned)numFrames, gy);
+  // identity maps (1:1 preview) and 16-byte aligned rows: the streaming kernel
+  const bool identity = outW == g.width && outH == g.height && (g.width & 7) == 0 && (outLine & 15) == 0
+                        && (previewStride & 15) == 0 && (((uintptr_t)previews) & 15) == 0 && (g.lineLength & 15) == 0
+                        && (g.frameStride & 15) == 0 && (((uintptr_t)frames) & 15) == 0
+                        && (long long)(g.width >> 3) * g.height * (g.width >> 3) < (1ll << 32);
+  if (identity)
+  {
+    const int cpr = g.width >> 3;
+    const uint32_t cprMagic = (uint32_t)((1ull << 32) / (uint32_t)cpr) + 1u;
+    const dim3 igrid((unsigned)(((long long)cpr * g.height + 255) / 256), (unsigned)(numFrames < 65535 ? numFrames : 65535));
+    const int colFirst = kind == KIND_OL ? 5 : 0, colLast = kind == KIND_OL ? g.width - 5 : g.width - 1;
+#define TRIK_PREVIEW_ID(K)                                                                                         \
+  preview_identity_kernel<K><<<igrid, 256, 0, stream>>>(g, frames, params, paramStride, bitmaps, outLine, previews,   \
+                                                        previewStride, numFrames, cprMagic, colFirst, colLast);       \
+  preview_overlay_kernel<K><<<(unsigned)numFrames, OVERLAY_THREADS, 0, stream>>>(g, params, paramStride, draw, omColours, pg, previews, previewStride)
+    switch (kind)
+    {
+      case KIND_WO: TRIK_PREVIEW_ID(KIND_WO); break;
+      case KIND_WL: TRIK_PREVIEW_ID(KIND_WL); break;
+      case KIND_OO: TRIK_PREVIEW_ID(KIND_OO); break;
+      case KIND_OL: TRIK_PREVIEW_ID(KIND_OL); break;
+      case KIND_OM: TRIK_PREVIEW_ID(KIND_OM); break;
+      default: return cudaErrorInvalidValue;
+    }
+#undef TRIK_PREVIEW_ID
+    g_launches_preview += 2;
+    return cudaGetLastError();
+  }
 #define TRIK_PREVIEW(K)                                                                                            \
   preview_base_kernel<K><<<grid, 256, 0, stream>>>(g, frames, params, paramStride, bitmaps, pg, previews, previewStride); \
-  preview_overlay_kernel<K><<<(unsigned)numFrames, 32, 0, stream>>>(g, params, paramStride, draw, omColours, pg, previews, previewStride)
+  preview_overlay_kernel<K><<<(unsigned)numFrames, OVERLAY_THREADS, 0, stream>>>(g, params, paramStride, draw, omColours, pg, previews, previewStride)
   switch (kind)
   {
     case KIND_WO: TRIK_PREVIEW(KIND_WO); break;
