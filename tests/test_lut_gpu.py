@@ -125,3 +125,41 @@ def test_skewed_table_layout_gives_the_same_bytes(size):
     finally:
         lib().trikb200_setLutSkew(1)
         codec.close()
+
+
+def test_batch_under_several_threshold_sets_takes_one_table_per_set():
+    """frames of one batch under DIFFERENT thresholds (per-stream thresholds gathered into one batch) used
+    to fall back to the arithmetic kernel.  Now the batch is partitioned by threshold set, one cached table and one launch
+    per set; results must be the per-frame results of the arithmetic path and of the oracle."""
+    from trik_media_sensors_dsp_b200 import launch_count
+    w, h, n = 320, 240, 400
+    sets = [THRESHOLDS[0], THRESHOLDS[1], THRESHOLDS[4], THRESHOLDS[7], THRESHOLDS[3]]
+    frames = synth.make_batch("scene", range(n), w, h, "yuyv")
+    arr = (xdm.RangeInArgsAlg * n)(*[xdm.RangeInArgsAlg(*sets[(i * 7) % len(sets)]) for i in range(n)])
+    codec = open_sensor("wo", w, h)
+    lib().trikb200_setLutMode(-1)                                   # the arithmetic kernel as the in-library comparison
+    ret, want = codec.process_batch(frames, arr)
+    assert ret == 0
+    lib().trikb200_setLutMode(0)
+    ret, got = codec.process_batch(frames, arr)                     # builds the five tables
+    assert ret == 0, lib().trikb200_lastError()
+    l0 = launch_count()
+    ret, got2 = codec.process_batch(frames, arr)                    # tables cached: five table-kernel launches, nothing else
+    assert ret == 0 and launch_count() - l0 == len(sets)
+    orc = oracle.OracleSensor("wo", w, h)
+    for i in range(n):
+        assert bytes(memoryview(got[i]))[:3] == bytes(memoryview(want[i]))[:3], i
+        assert bytes(memoryview(got2[i]))[:3] == bytes(memoryview(want[i]))[:3], i
+        if i % 9 == 0:
+            ok, exp = orc.process(frames[i], oracle.RangeInArgs(*sets[(i * 7) % len(sets)]))
+            assert ok == 1 and bytes(memoryview(got[i]))[:3] == bytes(memoryview(exp))[:3], i
+    # a set with fewer than 32 frames in the batch: the whole batch takes the arithmetic kernel, same bytes
+    arr3 = (xdm.RangeInArgsAlg * n)(*[xdm.RangeInArgsAlg(*(THRESHOLDS[5] if i == 17 else sets[i % 2])) for i in range(n)])
+    lib().trikb200_setLutMode(-1)
+    ret, want3 = codec.process_batch(frames, arr3)
+    lib().trikb200_setLutMode(0)
+    ret, got3 = codec.process_batch(frames, arr3)
+    assert ret == 0
+    for i in range(n):
+        assert bytes(memoryview(got3[i]))[:3] == bytes(memoryview(want3[i]))[:3], i
+    codec.close()

@@ -77,6 +77,10 @@ def main():
                 ia = xdm.MxnInArgsAlg(gm, gn)
             else:
                 ia = xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 40, 0)
+            # WOSETS=k: the webcam object sensor's frames under k different threshold sets, interleaved (per-frame arguments)
+            nsets = int(os.environ.get("WOSETS", "1"))
+            if kind == "wo" and nsets > 1:
+                ia = (xdm.RangeInArgsAlg * n)(*[xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 30 + 5 * (i % nsets), 0) for i in range(n)])
 
             # PREVIEW=1: with the RGB565X preview (1:1, device memory) as process() always produces it
             pv = torch.empty((n, fbytes), dtype=torch.uint8, device=dev) if os.environ.get("PREVIEW") == "1" else None
@@ -101,7 +105,7 @@ def main():
             gbs = n * w * h * 2 / (ms / 1e3) / 1e9
             print(json.dumps({"sensor": kind, "width": w, "height": h, "batch": n, "family": fam, "ms_per_batch": ms,
                               "frames_per_sec": n / (ms / 1e3), "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / peak,
-                              "launches_per_batch": (launch_count() - l0) / args.steps, "preview": pv is not None}), flush=True)
+                              "launches_per_batch": (launch_count() - l0) / args.steps, "preview": pv is not None, "wo_threshold_sets": nsets if kind == "wo" else None}), flush=True)
             codec.close()
             del d_frames, d_out
 

@@ -142,6 +142,15 @@ struct Instance {
   uint8_t*     dLutTable = nullptr; uint32_t* dLutMasks = nullptr;
   uint32_t     lutFrom = 0, lutTo = 0, lutExpected = 0; bool lutValid = false; cudaStream_t lutStream = nullptr;
   int          smCount = 0;
+  // further tables for batches whose frames come under several threshold sets (up to LUT_CACHE of them, least recently
+  // used replaced), and the frame lists of such a batch
+  struct LutSlot { uint8_t* table = nullptr; uint32_t* masks = nullptr; uint32_t from = 0, to = 0, expected = 0;
+                   bool valid = false; cudaStream_t stream = nullptr; unsigned long long lastUse = 0; };
+  static constexpr int LUT_CACHE = 8;
+  LutSlot      lutCache[LUT_CACHE];  unsigned long long lutClock = 0;
+  int*         hLutList = nullptr;  size_t hLutListCap = 0;
+  int*         dLutList = nullptr;  size_t dLutListCap = 0;
+  cudaEvent_t  hLutListFree = nullptr;
   // preview (RGB565X) support: index maps of this geometry, overlay inputs, staging image
   int32_t*     dHi2ho = nullptr;  int32_t* dWi2wo = nullptr;   // source row/col -> preview row/col
   int32_t*     dLastRow = nullptr; int32_t* dLastCol = nullptr; // preview row/col -> last source row/col (-1: none)
@@ -177,6 +186,10 @@ struct Instance {
     cudaFree(dFrames); dFrames = nullptr; dFramesCap = 0;
     cudaFree(dParams); dParams = nullptr; dParamsCap = 0;
     cudaFree(dLutTable); dLutTable = nullptr; cudaFree(dLutMasks); dLutMasks = nullptr; lutValid = false;
+    for (LutSlot& sl : lutCache) { cudaFree(sl.table); cudaFree(sl.masks); sl = LutSlot(); }
+    cudaFreeHost(hLutList); hLutList = nullptr; hLutListCap = 0;
+    cudaFree(dLutList); dLutList = nullptr; dLutListCap = 0;
+    if (hLutListFree) { cudaEventDestroy(hLutListFree); hLutListFree = nullptr; }
     cudaFree(dAcc);    dAcc = nullptr;    dAccCap = 0;
     cudaFree(dOut);    dOut = nullptr;    dOutCap = 0;
     cudaFree(dMxnTable); dMxnTable = nullptr;
@@ -496,6 +509,40 @@ bool ensure_lut(Instance* in, const FrameParams& fp, bool have, cudaStream_t s)
   return true;
 }
 
+// the table of one of several threshold sets of a batch: cached per handle, built on stream s when missing
+Instance::LutSlot* ensure_lut_slot(Instance* in, const FrameParams& fp, cudaStream_t s)
+{
+  Instance::LutSlot* victim = &in->lutCache[0];
+  for (Instance::LutSlot& sl : in->lutCache)
+  {
+    if (sl.valid && sl.stream == s && sl.from == fp.from && sl.to == fp.to && sl.expected == fp.expected)
+    {
+      sl.lastUse = ++in->lutClock;
+      return &sl;
+    }
+    if (sl.lastUse < victim->lastUse)
+      victim = &sl;
+  }
+  if (!victim->table)
+  {
+    if (cudaMalloc(&victim->table, LUT_TABLE_BYTES) != cudaSuccess || cudaMalloc(&victim->masks, LUT_MASK_BYTES) != cudaSuccess)
+    {
+      set_error("chroma table allocation", cudaGetLastError());
+      return nullptr;
+    }
+  }
+  victim->valid = false;
+  const cudaError_t e = launch_chroma_table(fp.from, fp.to, fp.expected, victim->table, victim->masks, s);
+  if (e != cudaSuccess)
+  {
+    set_error("launch_chroma_table", e);
+    return nullptr;
+  }
+  victim->from = fp.from; victim->to = fp.to; victim->expected = fp.expected;
+  victim->valid = true; victim->stream = s; victim->lastUse = ++in->lutClock;
+  return victim;
+}
+
 // the mxn colour-bin table of a device; built (and waited for, once) on first use so that every stream may read it
 const uint16_t* ensure_om_table(int device, cudaStream_t s)
 {
@@ -749,7 +796,59 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
         useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32) || (b.n >= 32 && lut_set_recurs(in, fp));
         if (useLut && !ensure_lut(in, fp, have, s)) return false;
       }
-      if (useLut)
+      // WO frames under SEVERAL threshold sets (per-stream thresholds gathered into one batch): partition the batch by set;
+      // when there are at most LUT_CACHE sets of at least 32 frames each, every set goes through its own cached table
+      bool multiLut = false;
+      std::vector<int> setOf, setFirst, setCount;
+      if (kind == KIND_WO && !broadcast && g_lutMode >= 0 && g.width % 8 == 0 && (b.n >= 256 || g_lutMode > 0))
+      {
+        setOf.resize((size_t)b.n);
+        multiLut = true;
+        for (int i = 0; multiLut && i < b.n; ++i)
+        {
+          int k = 0;
+          for (; k < (int)setFirst.size(); ++k)
+            if (std::memcmp(&in->paramsScratch[(size_t)setFirst[(size_t)k]], &in->paramsScratch[(size_t)i], sizeof(FrameParams)) == 0)
+              break;
+          if (k == (int)setFirst.size())
+          {
+            if (k == Instance::LUT_CACHE) { multiLut = false; break; }
+            setFirst.push_back(i); setCount.push_back(0);
+          }
+          setOf[(size_t)i] = k; ++setCount[(size_t)k];
+        }
+        for (size_t k = 0; multiLut && k < setCount.size(); ++k)
+          multiLut = setCount[k] >= 32;
+      }
+      if (multiLut)
+      {
+        if (!in->smCount)
+          CUDA_TRY(cudaDeviceGetAttribute(&in->smCount, cudaDevAttrMultiProcessorCount, in->device));
+        if (in->hLutListFree)
+          CUDA_TRY(cudaEventSynchronize(in->hLutListFree));
+        else
+          CUDA_TRY(cudaEventCreateWithFlags(&in->hLutListFree, cudaEventDisableTiming));
+        if (!in->grow_pinned(in->hLutList, in->hLutListCap, (size_t)b.n)) return false;
+        if (!in->grow_device(in->dLutList, in->dLutListCap, (size_t)b.n, false)) return false;
+        if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
+        std::vector<int> ofs(setCount.size() + 1, 0), fill(setCount.size(), 0);
+        for (size_t k = 0; k < setCount.size(); ++k) ofs[k + 1] = ofs[k] + setCount[k];
+        for (int i = 0; i < b.n; ++i)
+        {
+          const size_t k = (size_t)setOf[(size_t)i];
+          in->hLutList[ofs[k] + fill[k]++] = i;
+        }
+        CUDA_TRY(cudaMemcpyAsync(in->dLutList, in->hLutList, sizeof(int) * b.n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaEventRecord(in->hLutListFree, s));
+        for (size_t k = 0; k < setCount.size(); ++k)
+        {
+          Instance::LutSlot* sl = ensure_lut_slot(in, in->paramsScratch[(size_t)setFirst[k]], s);
+          if (!sl) return false;
+          CUDA_TRY(launch_wo_lut(g, setCount[k], dFrames, in->dParams + setFirst[k], sl->table, sl->masks,
+                                 reinterpret_cast<TargetOut*>(dOut), in->smCount, s, in->dAcc, in->dLutList + ofs[k]));
+        }
+      }
+      else if (useLut)
       {
         if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
         CUDA_TRY(launch_wo_lut(g, b.n, dFrames, in->dParams, in->dLutTable, in->dLutMasks,

@@ -118,7 +118,7 @@ cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, cons
                              unsigned long long* stats, cudaStream_t stream);
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                           const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream,
-                          SumAcc* acc = nullptr);
+                          SumAcc* acc = nullptr, const int* frameList = nullptr);   // frameList: numFrames frame indices
 void set_lut_parts(int parts);
 cudaError_t launch_line_bulk(bool planar, const Geometry& g, long long grid, int threads, const uint8_t* frames,
                              const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(1024, 1)
 wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
               const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
               const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi,
-              const int parts, const int rowsPerPart, SumAcc* __restrict__ acc)
+              const int parts, const int rowsPerPart, SumAcc* __restrict__ acc, const int* __restrict__ frameList)
 {
   constexpr uint32_t STRIDE = SKEW ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN;
   extern __shared__ __align__(16) uint8_t s_raw[];
@@ -198,8 +198,9 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   // a frame meet in its SumAcc record (zero between launches, as the sum kernels keep it) and the last one finalises.
   for (int item = blockIdx.x * groups + group; item < numFrames * parts; item += gridDim.x * groups)
   {
-    const int frame = parts == 1 ? item : item / parts;
-    const int row0 = parts == 1 ? 0 : (item - frame * parts) * rowsPerPart;
+    const int slot = parts == 1 ? item : item / parts;
+    const int row0 = parts == 1 ? 0 : (item - slot * parts) * rowsPerPart;
+    const int frame = frameList ? frameList[slot] : slot;  // a batch under several threshold sets: this set's frames
     const int rowsHere = min(rowsPerPart, g.height - row0);
     const int itersAll = rr < rowsHere ? (rowsHere - rr + rpi - 1) / rpi : 0;
     const uint8_t* fillPtr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)(row0 + rr) * g.lineLength;
@@ -480,7 +481,7 @@ cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, cons
 
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                           const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream,
-                          SumAcc* acc)
+                          SumAcc* acc, const int* frameList)
 {
   if (numFrames <= 0)
     return cudaSuccess;
@@ -529,9 +530,9 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
   if (e != cudaSuccess)
     return e;
   if (skew)
-    wo_lut_kernel<STAGES, true><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc);
+    wo_lut_kernel<STAGES, true><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc, frameList);
   else
-    wo_lut_kernel<STAGES, false><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc);
+    wo_lut_kernel<STAGES, false><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc, frameList);
   ++g_launches_lut;
   return cudaGetLastError();
 }
