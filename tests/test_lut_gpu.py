@@ -129,8 +129,8 @@ def test_skewed_table_layout_gives_the_same_bytes(size):
 
 def test_batch_under_several_threshold_sets_takes_one_table_per_set():
     """frames of one batch under DIFFERENT thresholds (per-stream thresholds gathered into one batch) used
-    to fall back to the arithmetic kernel.  Now the batch is partitioned by threshold set, one cached table and one launch
-    per set; results must be the per-frame results of the arithmetic path and of the oracle."""
+    to fall back to the arithmetic kernel.  Now the batch is partitioned by threshold set, one cached table per set and one
+    launch whose persistent CTAs are dealt out to the sets; results must be the per-frame results of the arithmetic path and of the oracle."""
     from trik_media_sensors_dsp_b200 import launch_count
     w, h, n = 320, 240, 400
     sets = [THRESHOLDS[0], THRESHOLDS[1], THRESHOLDS[4], THRESHOLDS[7], THRESHOLDS[3]]
@@ -144,8 +144,8 @@ def test_batch_under_several_threshold_sets_takes_one_table_per_set():
     ret, got = codec.process_batch(frames, arr)                     # builds the five tables
     assert ret == 0, lib().trikb200_lastError()
     l0 = launch_count()
-    ret, got2 = codec.process_batch(frames, arr)                    # tables cached: five table-kernel launches, nothing else
-    assert ret == 0 and launch_count() - l0 == len(sets)
+    ret, got2 = codec.process_batch(frames, arr)                    # tables cached: ONE launch, its CTAs dealt out to the sets
+    assert ret == 0 and launch_count() - l0 == 1
     orc = oracle.OracleSensor("wo", w, h)
     for i in range(n):
         assert bytes(memoryview(got[i]))[:3] == bytes(memoryview(want[i]))[:3], i

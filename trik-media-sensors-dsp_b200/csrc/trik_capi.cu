@@ -146,7 +146,7 @@ struct Instance {
   // used replaced), and the frame lists of such a batch
   struct LutSlot { uint8_t* table = nullptr; uint32_t* masks = nullptr; uint32_t from = 0, to = 0, expected = 0;
                    bool valid = false; cudaStream_t stream = nullptr; unsigned long long lastUse = 0; };
-  static constexpr int LUT_CACHE = 8;
+  static constexpr int LUT_CACHE = LUT_MAX_SETS;
   LutSlot      lutCache[LUT_CACHE];  unsigned long long lutClock = 0;
   int*         hLutList = nullptr;  size_t hLutListCap = 0;
   int*         dLutList = nullptr;  size_t dLutListCap = 0;
@@ -840,13 +840,17 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
         }
         CUDA_TRY(cudaMemcpyAsync(in->dLutList, in->hLutList, sizeof(int) * b.n, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaEventRecord(in->hLutListFree, s));
+        LutSets sets{};
+        sets.numSets = (int)setCount.size();
         for (size_t k = 0; k < setCount.size(); ++k)
         {
           Instance::LutSlot* sl = ensure_lut_slot(in, in->paramsScratch[(size_t)setFirst[k]], s);
           if (!sl) return false;
-          CUDA_TRY(launch_wo_lut(g, setCount[k], dFrames, in->dParams + setFirst[k], sl->table, sl->masks,
-                                 reinterpret_cast<TargetOut*>(dOut), in->smCount, s, in->dAcc, in->dLutList + ofs[k]));
+          sets.table[k] = sl->table; sets.masks[k] = sl->masks;
+          sets.listOffset[k] = ofs[k]; sets.count[k] = setCount[k]; sets.paramIndex[k] = setFirst[k];
         }
+        CUDA_TRY(launch_wo_lut_sets(g, dFrames, in->dParams, reinterpret_cast<TargetOut*>(dOut), in->smCount, s, in->dAcc,
+                                    in->dLutList, sets));
       }
       else if (useLut)
       {

@@ -120,6 +120,18 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
                           const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream,
                           SumAcc* acc = nullptr, const int* frameList = nullptr);   // frameList: numFrames frame indices
 void set_lut_parts(int parts);
+// the same for a batch under several threshold sets, in one launch: set k has count[k] frames, their indices at
+// frameList + listOffset[k], its FrameParams at params[paramIndex[k]] and its table / masks; the launcher fills the rest
+constexpr int LUT_MAX_SETS = 8;
+struct LutSets {
+  int numSets;
+  int ctaStart[LUT_MAX_SETS + 1];
+  const uint8_t* table[LUT_MAX_SETS];
+  const uint32_t* masks[LUT_MAX_SETS];
+  int listOffset[LUT_MAX_SETS], count[LUT_MAX_SETS], paramIndex[LUT_MAX_SETS], parts[LUT_MAX_SETS], rowsPerPart[LUT_MAX_SETS];
+};
+cudaError_t launch_wo_lut_sets(const Geometry& g, const uint8_t* frames, const FrameParams* params, TargetOut* out, int smCount,
+                               cudaStream_t stream, SumAcc* acc, const int* frameList, LutSets sets);
 cudaError_t launch_line_bulk(bool planar, const Geometry& g, long long grid, int threads, const uint8_t* frames,
                              const FrameParams* params, int paramStride, SumAcc* acc, TargetOut* out,
                              int slabs, int rowsPerSlab, int cpr, int rpi, int stages, bool overlap, cudaStream_t stream);

@@ -156,11 +156,12 @@ template <bool SKEW>
 __device__ __forceinline__ uint32_t lut_phys(uint32_t ci) { return SKEW ? ci + __umulhi(ci, 1u << 26) : ci; }
 
 template <int STAGES, bool SKEW>
-__global__ void __launch_bounds__(1024, 1)
-wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
-              const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
-              const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi,
-              const int parts, const int rowsPerPart, SumAcc* __restrict__ acc, const int* __restrict__ frameList)
+__device__ __forceinline__ void
+wo_lut_body(const Geometry& g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+            const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
+            const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi,
+            const int parts, const int rowsPerPart, SumAcc* __restrict__ acc, const int* __restrict__ frameList,
+            const int ctaIndex, const int ctaCount)
 {
   constexpr uint32_t STRIDE = SKEW ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN;
   extern __shared__ __align__(16) uint8_t s_raw[];
@@ -196,7 +197,7 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
   // A work item is one frame, or -- when whole frames would leave the last round of the persistent groups mostly empty
   // (1024 frames on 888 groups: two rounds for 1.15 rounds of work) -- one of `parts` bands of rowsPerPart rows; the bands of
   // a frame meet in its SumAcc record (zero between launches, as the sum kernels keep it) and the last one finalises.
-  for (int item = blockIdx.x * groups + group; item < numFrames * parts; item += gridDim.x * groups)
+  for (int item = ctaIndex * groups + group; item < numFrames * parts; item += ctaCount * groups)
   {
     const int slot = parts == 1 ? item : item / parts;
     const int row0 = parts == 1 ? 0 : (item - slot * parts) * rowsPerPart;
@@ -322,6 +323,33 @@ wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameP
     }
     group_barrier(1 + group, gthreads);                  // myRed is reused by the next frame
   }
+}
+
+template <int STAGES, bool SKEW>
+__global__ void __launch_bounds__(1024, 1)
+wo_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+              const uint8_t* __restrict__ table, const uint32_t* __restrict__ masks, TargetOut* __restrict__ out,
+              const int numFrames, const int groups, const int gthreads, const int cpr, const int rpi,
+              const int parts, const int rowsPerPart, SumAcc* __restrict__ acc, const int* __restrict__ frameList)
+{
+  wo_lut_body<STAGES, SKEW>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart,
+                            acc, frameList, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// One launch for a batch whose frames come under several threshold sets: the persistent CTAs are dealt out to the sets in
+// proportion to their frames, each CTA loads the table of ITS set and works through that set's frame list.
+template <int STAGES, bool SKEW>
+__global__ void __launch_bounds__(1024, 1)
+wo_lut_sets_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
+                   TargetOut* __restrict__ out, const int groups, const int gthreads, const int cpr, const int rpi,
+                   SumAcc* __restrict__ acc, const int* __restrict__ frameList, const LutSets sets)
+{
+  int k = 0;
+  while (k + 1 < sets.numSets && (int)blockIdx.x >= sets.ctaStart[k + 1])
+    ++k;
+  wo_lut_body<STAGES, SKEW>(g, frames, params + sets.paramIndex[k], sets.table[k], sets.masks[k], out, sets.count[k], groups,
+                            gthreads, cpr, rpi, sets.parts[k], sets.rowsPerPart[k], acc, frameList + sets.listOffset[k],
+                            (int)blockIdx.x - sets.ctaStart[k], sets.ctaStart[k + 1] - sets.ctaStart[k]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -479,6 +507,29 @@ cudaError_t launch_lut_check(uint32_t from, uint32_t to, uint32_t expected, cons
   return cudaGetLastError();
 }
 
+// bands per frame: the fewest of 1, 2, 4, 8 that fill the last round of `slots` persistent groups to 90 % (a band is at least
+// 2 * STAGES row iterations), else the best of them
+static int lut_bands(int numFrames, long long slots, int height, int rpi, int stages)
+{
+  int parts = 1;
+  if (g_lutParts == 1)
+    return 1;
+  double best = 0.0;
+  for (int cand = 1; cand <= 8; cand *= 2)
+  {
+    if (cand > 1 && height / cand < rpi * 2 * stages)
+      break;
+    if (g_lutParts > 1 && cand != g_lutParts)
+      continue;
+    const long long items = (long long)numFrames * cand;
+    const double eff = items <= slots ? 1.0 : (double)items / slots / (double)((items + slots - 1) / slots);
+    if (eff > best + 1e-9) { best = eff; parts = cand; }
+    if (eff >= 0.9)
+      break;
+  }
+  return parts;
+}
+
 cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                           const uint8_t* table, const uint32_t* masks, TargetOut* out, int smCount, cudaStream_t stream,
                           SumAcc* acc, const int* frameList)
@@ -503,24 +554,7 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
   const int threads = ((groups * gthreads + 31) / 32) * 32;
   // bands per frame: the fewest of 1, 2, 4, 8 that fill the last round of the persistent groups to 90 % (a band is at least
   // 2 * STAGES row iterations), else the best of them; needs the accumulator records
-  int parts = 1;
-  if (acc && g_lutParts != 1)
-  {
-    const long long slots = (long long)smCount * groups;
-    double best = 0.0;
-    for (int cand = 1; cand <= 8; cand *= 2)
-    {
-      if (cand > 1 && g.height / cand < rpi * 2 * STAGES)
-        break;
-      if (g_lutParts > 1 && cand != g_lutParts)
-        continue;
-      const long long items = (long long)numFrames * cand;
-      const double eff = items <= slots ? 1.0 : (double)items / slots / (double)((items + slots - 1) / slots);
-      if (eff > best + 1e-9) { best = eff; parts = cand; }
-      if (eff >= 0.9)
-        break;
-    }
-  }
+  const int parts = acc ? lut_bands(numFrames, (long long)smCount * groups, g.height, rpi, STAGES) : 1;
   const int rowsPerPart = (((g.height + parts - 1) / parts + rpi - 1) / rpi) * rpi;     // whole row iterations per band
   int grid = (int)(((long long)numFrames * parts + groups - 1) / groups);
   if (grid > smCount) grid = smCount;
@@ -533,6 +567,66 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
     wo_lut_kernel<STAGES, true><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc, frameList);
   else
     wo_lut_kernel<STAGES, false><<<grid, threads, smem, stream>>>(g, frames, params, table, masks, out, numFrames, groups, gthreads, cpr, rpi, parts, rowsPerPart, acc, frameList);
+  ++g_launches_lut;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wo_lut_sets(const Geometry& g, const uint8_t* frames, const FrameParams* params, TargetOut* out, int smCount,
+                               cudaStream_t stream, SumAcc* acc, const int* frameList, LutSets sets)
+{
+  if (sets.numSets <= 0 || sets.numSets > LUT_MAX_SETS || !acc || !frameList)
+    return cudaErrorInvalidValue;
+  const int gthreads = sum_sensor_block_threads(KIND_WO, g.width);
+  if (gthreads <= 0 || gthreads > 1024)
+    return cudaErrorInvalidValue;
+  const int cpr = g.width / 8;
+  const int rpi = gthreads / cpr;
+  constexpr int STAGES = 4;
+  int groups = 1024 / gthreads;
+  if (groups > 15) groups = 15;
+  const bool skew = g_lutSkew != 0;
+  const size_t tableBytes = 2u * (skew ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN);
+  auto smem_for = [&](int ng) { return tableBytes + (size_t)STAGES * ng * gthreads * 16 + (size_t)ng * 128 * 4; };
+  while (groups > 1 && smem_for(groups) > 220 * 1024) --groups;
+  if (smem_for(groups) > 227 * 1024)
+    return cudaErrorInvalidValue;
+  const int threads = ((groups * gthreads + 31) / 32) * 32;
+  // the SMs (one persistent CTA each) dealt out in proportion to the sets' frames, at least one per set
+  long long total = 0;
+  for (int k = 0; k < sets.numSets; ++k) total += sets.count[k];
+  if (total <= 0)
+    return cudaSuccess;
+  int ctas[LUT_MAX_SETS], used = 0, biggest = 0;
+  for (int k = 0; k < sets.numSets; ++k)
+  {
+    ctas[k] = (int)((long long)smCount * sets.count[k] / total);
+    if (ctas[k] < 1) ctas[k] = 1;
+    const int need = (sets.count[k] + groups - 1) / groups;           // no more CTAs than whole-frame items
+    if (ctas[k] > need * 8) ctas[k] = need * 8;
+    used += ctas[k];
+    if (sets.count[k] > sets.count[biggest]) biggest = k;
+  }
+  if (used < smCount)
+    ctas[biggest] += smCount - used;
+  sets.ctaStart[0] = 0;
+  for (int k = 0; k < sets.numSets; ++k)
+  {
+    sets.parts[k] = lut_bands(sets.count[k], (long long)ctas[k] * groups, g.height, rpi, STAGES);
+    sets.rowsPerPart[k] = (((g.height + sets.parts[k] - 1) / sets.parts[k] + rpi - 1) / rpi) * rpi;
+    const int need = (int)(((long long)sets.count[k] * sets.parts[k] + groups - 1) / groups);
+    if (ctas[k] > need) ctas[k] = need;
+    sets.ctaStart[k + 1] = sets.ctaStart[k] + ctas[k];
+  }
+  const int grid = sets.ctaStart[sets.numSets];
+  const size_t smem = smem_for(groups);
+  cudaError_t e = skew ? cudaFuncSetAttribute(wo_lut_sets_kernel<STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(wo_lut_sets_kernel<STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  if (skew)
+    wo_lut_sets_kernel<STAGES, true><<<grid, threads, smem, stream>>>(g, frames, params, out, groups, gthreads, cpr, rpi, acc, frameList, sets);
+  else
+    wo_lut_sets_kernel<STAGES, false><<<grid, threads, smem, stream>>>(g, frames, params, out, groups, gthreads, cpr, rpi, acc, frameList, sets);
   ++g_launches_lut;
   return cudaGetLastError();
 }
