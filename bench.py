@@ -271,6 +271,20 @@ def extras(line, args, torch, dev, stream, sptr, timed, peak, sampler_factory):
             name = kind if not grid or grid == (3, 3) else "%s_%dx%d" % (kind, grid[0], grid[1])
             out[name] = {"frames_per_sec": n / (ms / 1000.0), "ms_per_step": ms, "hbm_frac": n * fb / (ms / 1000.0) / 1e9 / peak,
                          "frames": fam, "batch": n}
+            if kind == "wo":
+                # the same frames under 8 different threshold sets (per-frame arguments, interleaved): one launch, a table per set
+                arr = (xdm.RangeInArgsAlg * n)(*[xdm.RangeInArgsAlg(0, 359, 0, 100, 0, 30 + 5 * (i % 8), 0) for i in range(n)])
+
+                def sstep():
+                    r, _ = oc.process_batch(d_frames.data_ptr(), arr, frames_device=True, frame_stride=fb, num_frames=n,
+                                            out_device_ptr=o_out.data_ptr(), stream=sptr, flags=xdm.BATCH_ASYNC)
+                    assert r == 0, _sensors.last_error()
+
+                for _ in range(3):
+                    sstep()
+                sms = timed(sstep, 10) / 10
+                out["wo_8_threshold_sets"] = {"frames_per_sec": n / (sms / 1000.0), "ms_per_step": sms,
+                                              "hbm_frac": n * fb / (sms / 1000.0) / 1e9 / peak, "frames": fam, "batch": n}
             if kind in ("wl", "oo"):
                 # the RGB565X preview with overlays, written to device memory at 1:1: 2 B/px read + 2 B/px written
                 pv = torch.empty((n, fb), dtype=torch.uint8, device=dev)

@@ -354,6 +354,10 @@ void trikb200_setLutSkew(XDAS_Int32 on);
 /* tuning knob: work items of the webcam object sensor's table kernel: 0 (default) = whole frames, or 2 / 4 / 8 bands of rows
  * per frame when whole frames would leave the last round of the persistent groups mostly idle; 1 / 2 / 4 / 8 = fixed */
 void trikb200_setLutParts(XDAS_Int32 parts);
+/* tuning knob: a batch with 1:1 previews can go through the preview kernels in sub-batches whose images total about this
+ * many MiB (so that the overlay kernel's scattered two-byte stores land on lines still in L2); measured slower than the whole
+ * batch at once at every size tried, hence 0 (= the whole batch at once) is the default */
+void trikb200_setPreviewChunkMB(XDAS_Int32 mb);
 /* tuning knob: edge-line kernel, 0 = packed four-pixels-per-thread form (default, needs 4-byte aligned rows), 1 = one thread
  * per column (first version) */
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant);

@@ -86,3 +86,34 @@ def test_batch_previews_equal_single_calls():
         assert r == 0
         assert np.array_equal(codec.preview[:160 * 120 * 2], prev[i])
     codec.close()
+
+
+@pytest.mark.parametrize("kind", xdm.KIND_NAMES)
+def test_one_to_one_batch_previews_in_sub_batches(kind):
+    """1:1 previews of a batch go through the streaming kernel in sub-batches (so that the overlay stores hit L2): the
+    images must not depend on the sub-batch size, and must equal single process() calls (which the test above pins to
+    the reference's drawing)."""
+    w, h, n = 320, 240, 21
+    layout = sensors.layout_of(xdm.KIND_OF[kind])
+    fam = "grid" if kind == "om" else "blobs" if kind == "oo" else "scene"
+    frames = np.stack([synth.make_frame(fam, s, w, h, layout) for s in range(n)])
+    ia = xdm.IN_ARGS_ALG[xdm.KIND_OF[kind]](*args_for(kind, 0))
+    L = sensors.lib()
+    images = []
+    try:
+        for mb in (0, 1, 40):                      # whole batch at once (the default) / 8-frame sub-batches / 40 MiB
+            L.trikb200_setPreviewChunkMB(mb)
+            codec = open_sensor(kind, w, h, out_w=w, out_h=h)
+            prev = np.full((n, w * h * 2), 0xAB, dtype=np.uint8)
+            ret, outs = codec.process_batch(frames, ia, previews=prev)
+            assert ret == 0, sensors.last_error()
+            images.append(prev)
+            codec.close()
+    finally:
+        L.trikb200_setPreviewChunkMB(0)
+    assert np.array_equal(images[0], images[1]) and np.array_equal(images[0], images[2])
+    codec = open_sensor(kind, w, h, out_w=w, out_h=h)
+    for i in range(n):
+        r, oa = codec.process(frames[i], ia)
+        assert r == 0 and np.array_equal(codec.preview[:w * h * 2], images[0][i]), (kind, i)
+    codec.close()

@@ -23,6 +23,8 @@ namespace trikb200 {
 
 extern std::atomic<long long> g_launches_preview;
 std::atomic<long long> g_launches_preview{0};
+static long long g_previewChunkBytes = 0;                // images of one sub-batch of a 1:1 preview pass (0 = whole batch at once, the default)
+void set_preview_chunk_bytes(long long bytes) { g_previewChunkBytes = bytes; }
 
 __device__ __forceinline__ uint16_t rgb565x(uint32_t rgb888)           // writeOutputPixel (:66-70)
 {
@@ -391,21 +393,46 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
     const uint32_t cprMagic = (uint32_t)((1ull << 32) / (uint32_t)cpr) + 1u;
     const dim3 igrid((unsigned)(((long long)cpr * g.height + 255) / 256), (unsigned)(numFrames < 65535 ? numFrames : 65535));
     const int colFirst = kind == KIND_OL ? 5 : 0, colLast = kind == KIND_OL ? g.width - 5 : g.width - 1;
-#define TRIK_PREVIEW_ID(K)                                                                                         \
-  preview_identity_kernel<K><<<igrid, 256, 0, stream>>>(g, frames, params, paramStride, bitmaps, outLine, previews,   \
-                                                        previewStride, numFrames, cprMagic, colFirst, colLast);       \
-  preview_overlay_kernel<K><<<(unsigned)numFrames, OVERLAY_THREADS, 0, stream>>>(g, params, paramStride, draw, omColours, pg, previews, previewStride)
-    switch (kind)
+    // The overlay kernel's stores are two bytes each, nearly every one in a sector of its own: on an image that has left
+    // L2 each costs a sector fill and a write-back (measured: 112 us for 1024 x 640x480, 1 % of the issue slots used).
+    // Sub-batches whose images fit in L2 together (so that the overlay lands on lines the base-layer kernel has just written)
+    // were measured and are SLOWER at every size tried -- 1024 x 640x480 WL: 0.500 ms at once, 0.506 / 0.516 / 0.573 / 0.753 ms
+    // with 96 / 64 / 40 / 20 MiB sub-batches (the kernel boundaries cost more than the L2 hits save) -- so the default is the
+    // whole batch at once; the knob stays for measurements (profiles/r02m_sweep_preview_chunks.jsonl).
+    const size_t perFrame = (size_t)outH * outLine;
+    int chunk = numFrames;
+    if (g_previewChunkBytes > 0 && perFrame > 0)
     {
-      case KIND_WO: TRIK_PREVIEW_ID(KIND_WO); break;
-      case KIND_WL: TRIK_PREVIEW_ID(KIND_WL); break;
-      case KIND_OO: TRIK_PREVIEW_ID(KIND_OO); break;
-      case KIND_OL: TRIK_PREVIEW_ID(KIND_OL); break;
-      case KIND_OM: TRIK_PREVIEW_ID(KIND_OM); break;
-      default: return cudaErrorInvalidValue;
+      chunk = (int)(g_previewChunkBytes / perFrame);
+      if (chunk < 8) chunk = 8;
     }
+    const size_t cells = (size_t)(g.width >> 2) * (g.height >> 2);
+    for (int f0 = 0; f0 < numFrames; f0 += chunk)
+    {
+      const int cnt = numFrames - f0 < chunk ? numFrames - f0 : chunk;
+      const dim3 cgrid(igrid.x, (unsigned)(cnt < 65535 ? cnt : 65535));
+      const uint8_t* cf = frames + (size_t)f0 * g.frameStride;
+      const FrameParams* cp = params + (size_t)f0 * paramStride;
+      const uint16_t* cb = bitmaps ? bitmaps + (size_t)f0 * cells : nullptr;
+      const DrawInfo* cd = draw ? draw + f0 : nullptr;
+      const int32_t* co = omColours ? omColours + (size_t)f0 * 100 : nullptr;
+      uint8_t* cpv = previews + (size_t)f0 * previewStride;
+#define TRIK_PREVIEW_ID(K)                                                                                         \
+  preview_identity_kernel<K><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,                      \
+                                                        previewStride, cnt, cprMagic, colFirst, colLast);              \
+  preview_overlay_kernel<K><<<(unsigned)cnt, OVERLAY_THREADS, 0, stream>>>(g, cp, paramStride, cd, co, pg, cpv, previewStride)
+      switch (kind)
+      {
+        case KIND_WO: TRIK_PREVIEW_ID(KIND_WO); break;
+        case KIND_WL: TRIK_PREVIEW_ID(KIND_WL); break;
+        case KIND_OO: TRIK_PREVIEW_ID(KIND_OO); break;
+        case KIND_OL: TRIK_PREVIEW_ID(KIND_OL); break;
+        case KIND_OM: TRIK_PREVIEW_ID(KIND_OM); break;
+        default: return cudaErrorInvalidValue;
+      }
 #undef TRIK_PREVIEW_ID
-    g_launches_preview += 2;
+      g_launches_preview += 2;
+    }
     return cudaGetLastError();
   }
 #define TRIK_PREVIEW(K)                                                                                            \
