@@ -160,6 +160,7 @@ struct Instance {
   FrameParams* hParams = nullptr;   size_t hParamsCap = 0;
   cudaEvent_t  hParamsFree = nullptr;                          // completes when the last upload has read hParams
   std::vector<FrameParams> paramsScratch;                      // a batch's parameters before they are staged
+  std::vector<int> argSetScratch;                              // ... and, for the webcam sensors, which distinct argument set each frame uses
   // the single broadcast record dParams[0] currently holds, and the stream that uploaded it
   FrameParams  dBroadcast = {};     bool dBroadcastValid = false;  cudaStream_t dBroadcastStream = nullptr;
   uint8_t*     hOut = nullptr;      size_t hOutCap = 0;
@@ -614,24 +615,59 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
   if (b.streamIds && (int)in->streamStates.size() < b.numStreams)
     in->streamStates.resize((size_t)b.numStreams);
   size_t np = broadcast ? 1 : (size_t)b.n;
-  in->paramsScratch.assign(np, FrameParams{});
+  in->paramsScratch.resize(np);
+  // The webcam sensors carry no state: their parameters are a function of the argument bytes alone, and a batch usually
+  // holds a handful of distinct argument sets (per-camera thresholds).  The first LUT_MAX_SETS distinct ones are remembered
+  // with their parameters, so a frame costs one short compare instead of the conversion, and its set number falls out for
+  // the table path below (argSet[i], -1 once a batch has more sets than that).
+  const bool stateless = kind == KIND_WO || kind == KIND_WL;
+  struct ArgMemo { uint8_t bytes[sizeof(TRIKB200_RangeInArgsAlg)]; FrameParams fp; };
+  ArgMemo memo[LUT_MAX_SETS];
+  int numMemo = 0;
+  bool memoComplete = stateless && !broadcast;           // every frame's set is known
+  std::vector<int>& argSet = in->argSetScratch;
+  if (memoComplete)
+    argSet.resize(np);
   for (size_t i = 0; i < np; ++i)
-    prepare_frame_params(kind, in->geo, b.in_args((int)i),
+  {
+    const uint8_t* ia = b.in_args((int)i);
+    if (stateless && !broadcast)
+    {
+      int k = 0;
+      for (; k < numMemo; ++k)
+        if (std::memcmp(memo[k].bytes, ia, sizeof(memo[k].bytes)) == 0)
+          break;
+      if (k < numMemo)
+      {
+        in->paramsScratch[i] = memo[k].fp;
+        argSet[i] = k;
+        continue;
+      }
+      prepare_frame_params(kind, in->geo, ia, in->state, in->paramsScratch[i]);
+      if (numMemo < LUT_MAX_SETS)
+      {
+        std::memcpy(memo[numMemo].bytes, ia, sizeof(memo[numMemo].bytes));
+        memo[numMemo].fp = in->paramsScratch[i];
+        argSet[i] = numMemo++;
+      }
+      else
+      {
+        memoComplete = false;
+        argSet[i] = -1;
+      }
+      continue;
+    }
+    prepare_frame_params(kind, in->geo, ia,
                          b.statePtrs ? *b.statePtrs[i] : b.streamIds ? in->streamStates[(size_t)b.streamIds[i]] : in->state,
                          in->paramsScratch[i]);
+  }
   // A per-frame array (or pointer list) of arguments that all say the same thing is a broadcast: one record, and the
   // chroma-table path of the webcam object sensor stays available (a batch gathered from many handles looks like this).
-  if (!broadcast && (kind == KIND_WO || kind == KIND_WL) && np > 1)
+  if (memoComplete && numMemo == 1 && np > 1)
   {
-    bool same = true;
-    for (size_t i = 1; same && i < np; ++i)
-      same = std::memcmp(&in->paramsScratch[0], &in->paramsScratch[i], sizeof(FrameParams)) == 0;
-    if (same)
-    {
-      broadcast = true;
-      np = 1;
-      in->paramsScratch.resize(1);
-    }
+    broadcast = true;
+    np = 1;
+    in->paramsScratch.resize(1);
   }
   const FrameParams* const dParamsBefore = in->dParams;
   if (!in->grow_device(in->dParams, in->dParamsCap, np, false)) return false;
@@ -799,24 +835,18 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       // WO frames under SEVERAL threshold sets (per-stream thresholds gathered into one batch): partition the batch by set;
       // when there are at most LUT_CACHE sets of at least 32 frames each, every set goes through its own cached table
       bool multiLut = false;
-      std::vector<int> setOf, setFirst, setCount;
-      if (kind == KIND_WO && !broadcast && g_lutMode >= 0 && g.width % 8 == 0 && (b.n >= 256 || g_lutMode > 0))
+      std::vector<int> setFirst, setCount;
+      const std::vector<int>& setOf = argSet;
+      if (kind == KIND_WO && !broadcast && memoComplete && g_lutMode >= 0 && g.width % 8 == 0 && (b.n >= 256 || g_lutMode > 0))
       {
-        setOf.resize((size_t)b.n);
-        multiLut = true;
-        for (int i = 0; multiLut && i < b.n; ++i)
+        setFirst.assign((size_t)numMemo, -1); setCount.assign((size_t)numMemo, 0);
+        for (int i = 0; i < b.n; ++i)
         {
-          int k = 0;
-          for (; k < (int)setFirst.size(); ++k)
-            if (std::memcmp(&in->paramsScratch[(size_t)setFirst[(size_t)k]], &in->paramsScratch[(size_t)i], sizeof(FrameParams)) == 0)
-              break;
-          if (k == (int)setFirst.size())
-          {
-            if (k == Instance::LUT_CACHE) { multiLut = false; break; }
-            setFirst.push_back(i); setCount.push_back(0);
-          }
-          setOf[(size_t)i] = k; ++setCount[(size_t)k];
+          const size_t k = (size_t)setOf[(size_t)i];
+          if (setFirst[k] < 0) setFirst[k] = i;
+          ++setCount[k];
         }
+        multiLut = true;
         for (size_t k = 0; multiLut && k < setCount.size(); ++k)
           multiLut = setCount[k] >= 32;
       }
