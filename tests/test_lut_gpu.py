@@ -163,3 +163,40 @@ def test_batch_under_several_threshold_sets_takes_one_table_per_set():
     for i in range(n):
         assert bytes(memoryview(got3[i]))[:3] == bytes(memoryview(want3[i]))[:3], i
     codec.close()
+
+
+def test_oo_batch_under_several_ranges_takes_the_tables():
+    """object sensor frames whose ranges differ inside one batch (instances gathered by trikb200_processMixed, or a batch that
+    re-sets the range now and then): step 1 through one cached table per range, in one launch; same bytes as the arithmetic
+    step 1 and as the oracle"""
+    from trik_media_sensors_dsp_b200 import launch_count
+    w, h, n = 320, 240, 320
+    ranges = [(1, 0, 20, 80, 20, 50, 30, 0), (1, 200, 45, 55, 40, 50, 45, 0), (1, 120, 60, 50, 50, 50, 50, 0)]
+    frames = np.stack([synth.make_frame("blobs" if i % 2 else "scene", i, w, h, "yuv422p") for i in range(n)])
+    # every 40 frames the range is set anew (cycling through the three), in between it is the carried one
+    arr = (xdm.ObjInArgsAlg * n)(*[xdm.ObjInArgsAlg(*ranges[(i // 40) % 3]) if i % 40 == 0 else xdm.ObjInArgsAlg(0, 0, 0, 0, 0, 0, 0, 0)
+                                   for i in range(n)])
+    codec = open_sensor("oo", w, h)
+    lib().trikb200_setLutMode(-1)
+    ret, want = codec.process_batch(frames, arr)
+    assert ret == 0
+    lib().trikb200_setLutMode(0)
+    codec2 = open_sensor("oo", w, h)
+    ret, got = codec2.process_batch(frames, arr)
+    assert ret == 0, lib().trikb200_lastError()
+    codec3 = open_sensor("oo", w, h)
+    ret, _ = codec3.process_batch(frames, arr)
+    l0 = launch_count()
+    codec3.set_params(w, h)
+    ret, got3 = codec3.process_batch(frames, arr)              # tables cached: step 1 + labelling, two launches
+    assert ret == 0 and launch_count() - l0 == 2
+    orc = oracle.OracleSensor("oo", w, h)
+    for i in range(n):
+        assert bytes(memoryview(got[i]))[:24] == bytes(memoryview(want[i]))[:24], i
+        assert bytes(memoryview(got3[i]))[:24] == bytes(memoryview(want[i]))[:24], i
+        a = ranges[(i // 40) % 3] if i % 40 == 0 else (0, 0, 0, 0, 0, 0, 0, 0)
+        ok, exp = orc.process(frames[i], oracle.ObjInArgs(*a))
+        if not orc.last_flags():
+            assert ok == 1 and bytes(memoryview(got[i]))[:24] == bytes(memoryview(exp))[:24], i
+    for c in (codec, codec2, codec3):
+        c.close()

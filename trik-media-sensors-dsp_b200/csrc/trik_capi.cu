@@ -947,8 +947,67 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
         useLut = g_lutMode > 0 || b.n >= 256 || (have && b.n >= 32) || (b.n >= 32 && lut_set_recurs(in, fp0));
         if (useLut && !ensure_lut(in, fp0, have, s)) return false;
       }
+      // frames under several ranges (object sensor instances gathered into one batch, each carrying its own range): up to
+      // LUT_MAX_SETS ranges of at least 32 frames each go through their cached tables in one step-1 launch
+      LutSets sets{};
+      bool multiLut = false;
+      if (!useLut && g_lutMode >= 0 && (b.n >= 256 || g_lutMode > 0) && g.width / 16 <= 768)
+      {
+        std::vector<int>& setOf = in->argSetScratch;
+        setOf.resize((size_t)b.n);
+        int setFirst[LUT_MAX_SETS], setCount[LUT_MAX_SETS], numSets = 0;
+        multiLut = true;
+        for (int i = 0; multiLut && i < b.n; ++i)
+        {
+          const FrameParams& fp = in->paramsScratch[(size_t)i];
+          int k = 0;
+          for (; k < numSets; ++k)
+          {
+            const FrameParams& f0 = in->paramsScratch[(size_t)setFirst[k]];
+            if (f0.from == fp.from && f0.to == fp.to && f0.expected == fp.expected)
+              break;
+          }
+          if (k == numSets)
+          {
+            if (numSets == LUT_MAX_SETS) { multiLut = false; break; }
+            setFirst[numSets] = i; setCount[numSets] = 0; ++numSets;
+          }
+          setOf[(size_t)i] = k; ++setCount[k];
+        }
+        for (int k = 0; multiLut && k < numSets; ++k)
+          multiLut = setCount[k] >= 32;
+        if (multiLut)
+        {
+          if (!in->smCount)
+            CUDA_TRY(cudaDeviceGetAttribute(&in->smCount, cudaDevAttrMultiProcessorCount, in->device));
+          if (in->hLutListFree)
+            CUDA_TRY(cudaEventSynchronize(in->hLutListFree));
+          else
+            CUDA_TRY(cudaEventCreateWithFlags(&in->hLutListFree, cudaEventDisableTiming));
+          if (!in->grow_pinned(in->hLutList, in->hLutListCap, (size_t)b.n)) return false;
+          if (!in->grow_device(in->dLutList, in->dLutListCap, (size_t)b.n, false)) return false;
+          int ofs[LUT_MAX_SETS + 1] = {0}, fill[LUT_MAX_SETS] = {0};
+          for (int k = 0; k < numSets; ++k) ofs[k + 1] = ofs[k] + setCount[k];
+          for (int i = 0; i < b.n; ++i)
+          {
+            const int k = setOf[(size_t)i];
+            in->hLutList[ofs[k] + fill[k]++] = i;
+          }
+          CUDA_TRY(cudaMemcpyAsync(in->dLutList, in->hLutList, sizeof(int) * b.n, cudaMemcpyHostToDevice, s));
+          CUDA_TRY(cudaEventRecord(in->hLutListFree, s));
+          sets.numSets = numSets;
+          for (int k = 0; k < numSets; ++k)
+          {
+            Instance::LutSlot* sl = ensure_lut_slot(in, in->paramsScratch[(size_t)setFirst[k]], s);
+            if (!sl) return false;
+            sets.table[k] = sl->table; sets.masks[k] = sl->masks;
+            sets.listOffset[k] = ofs[k]; sets.count[k] = setCount[k]; sets.paramIndex[k] = setFirst[k];
+          }
+        }
+      }
       CUDA_TRY(launch_oo(g, b.n, dFrames, in->dParams, pstride, in->dBitmaps, in->dClusters, in->dEqual, maxLabels, dOut, nullptr, s,
-                         useLut ? in->dLutTable : nullptr, in->dLutMasks, in->smCount));
+                         useLut ? in->dLutTable : nullptr, in->dLutMasks, in->smCount,
+                         multiLut ? in->dLutList : nullptr, multiLut ? &sets : nullptr));
       break;
     }
     default:

@@ -72,11 +72,14 @@ cudaError_t launch_om(const Geometry& g, int numFrames, const uint8_t* frames, c
                       cudaStream_t stream);
 // OO: bitmaps = numFrames x (W/4)(H/4) uint16; clusters = numFrames x maxLabels x 12 bytes;
 // equal = numFrames x maxLabels uint16; out = numFrames x 36-byte ObjOutArgsAlg records
-// lutTable != nullptr: all frames share one threshold set and step 1 goes through its chroma table
+// lutTable != nullptr: all frames share one threshold set and step 1 goes through its chroma table;
+// lutSets != nullptr: the frames come under several sets, each with its table and its frame list (see LutSets below)
+struct LutSets;
 cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                       int paramStride, uint16_t* bitmaps, void* clusters, uint16_t* equal, int maxLabels,
                       void* out, int* labelCounts, cudaStream_t stream,
-                      const uint8_t* lutTable = nullptr, const uint32_t* lutMasks = nullptr, int smCount = 0);
+                      const uint8_t* lutTable = nullptr, const uint32_t* lutMasks = nullptr, int smCount = 0,
+                      const int* lutFrameList = nullptr, const LutSets* lutSets = nullptr);
 inline int oo_max_labels(int width, int height) { return ((width / 4) / 2 + 1) * ((height / 4) / 2 + 1) + 2; }
 
 // auto-calibration histograms over the frames listed in frameIdx (device array of numFlagged indices)
@@ -131,6 +134,8 @@ struct LutSets {
   const uint32_t* masks[LUT_MAX_SETS];
   int listOffset[LUT_MAX_SETS], count[LUT_MAX_SETS], paramIndex[LUT_MAX_SETS], parts[LUT_MAX_SETS], rowsPerPart[LUT_MAX_SETS];
 };
+cudaError_t launch_oo_bitmap_lut_sets(const Geometry& g, const uint8_t* frames, uint16_t* bitmaps, int smCount,
+                                      cudaStream_t stream, const int* frameList, LutSets sets);
 cudaError_t launch_wo_lut_sets(const Geometry& g, const uint8_t* frames, const FrameParams* params, TargetOut* out, int smCount,
                                cudaStream_t stream, SumAcc* acc, const int* frameList, LutSets sets);
 cudaError_t launch_line_bulk(bool planar, const Geometry& g, long long grid, int threads, const uint8_t* frames,

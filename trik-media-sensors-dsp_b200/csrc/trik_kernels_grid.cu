@@ -825,7 +825,8 @@ oo_cluster_kernel(const Geometry g, const uint16_t* __restrict__ bitmaps, OoClus
 cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, const FrameParams* params,
                       int paramStride, uint16_t* bitmaps, void* clusters, uint16_t* equal, int maxLabels,
                       void* out, int* labelCounts, cudaStream_t stream,
-                      const uint8_t* lutTable, const uint32_t* lutMasks, int smCount)
+                      const uint8_t* lutTable, const uint32_t* lutMasks, int smCount,
+                      const int* lutFrameList, const LutSets* lutSets)
 {
   if (numFrames <= 0)
     return cudaSuccess;
@@ -842,7 +843,9 @@ cudaError_t launch_oo(const Geometry& g, int numFrames, const uint8_t* frames, c
   if (slabs > 65535) slabs = 65535;
   dim3 grid((unsigned)numFrames, (unsigned)slabs);
   cudaError_t e;
-  if (viaTable)
+  if (lutSets && lutFrameList && cpr <= 768)
+    e = launch_oo_bitmap_lut_sets(g, frames, bitmaps, smCount, stream, lutFrameList, *lutSets);
+  else if (viaTable)
     e = launch_oo_bitmap_lut(g, numFrames, frames, lutTable, lutMasks, bitmaps, smCount, stream);
   else
   {

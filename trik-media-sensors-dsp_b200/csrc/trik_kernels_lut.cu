@@ -359,10 +359,11 @@ wo_lut_sets_kernel(const Geometry g, const uint8_t* __restrict__ frames, const F
 // 16-pixel luma chunk: 4 rows x (16 luma + 16 chroma bytes), one 8-byte store.  Persistent CTAs (table in shared
 // memory, one per SM), blockDim = cpr * rows: `rows` metapixel rows of the batch at a time, no barrier needed.
 template <bool SKEW>
-__global__ void __launch_bounds__(768, 1)
-oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ table,
-                     const uint32_t* __restrict__ masks, uint16_t* __restrict__ bitmaps,
-                     const int numFrames, const int cpr, const int rows)
+__device__ __forceinline__ void
+oo_bitmap_lut_body(const Geometry& g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ table,
+                   const uint32_t* __restrict__ masks, uint16_t* __restrict__ bitmaps,
+                   const int numFrames, const int cpr, const int rows, const int* __restrict__ frameList,
+                   const int ctaIndex, const int ctaCount)
 {
   constexpr uint32_t STRIDE = SKEW ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN;
   extern __shared__ __align__(16) uint8_t s_raw[];
@@ -382,10 +383,11 @@ oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const
   const size_t chromaOfs = (size_t)g.height * g.lineLength;
   const long long units = (long long)numFrames * bh;                 // (frame, metapixel row)
 
-  for (long long u = (long long)blockIdx.x * rows + rr; u < units; u += (long long)gridDim.x * rows)
+  for (long long u = (long long)ctaIndex * rows + rr; u < units; u += (long long)ctaCount * rows)
   {
-    const int frame = (int)(u / bh);
-    const int mr = (int)(u - (long long)frame * bh);
+    const int slot = (int)(u / bh);
+    const int mr = (int)(u - (long long)slot * bh);
+    const int frame = frameList ? frameList[slot] : slot;            // a batch under several ranges: this range's frames
     const uint8_t* ptr = frames + (size_t)frame * g.frameStride + (size_t)cc * 16u + (size_t)(mr * 4) * g.lineLength;
     uint4 lu[4], ch[4];
 #pragma unroll
@@ -437,6 +439,76 @@ oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const
     v.y = (meta[2] & 0xFFFFu) | (meta[3] << 16);
     *reinterpret_cast<uint2*>(bitmaps + ((size_t)frame * bh + mr) * bw + cc * 4) = v;
   }
+}
+
+template <bool SKEW>
+__global__ void __launch_bounds__(768, 1)
+oo_bitmap_lut_kernel(const Geometry g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ table,
+                     const uint32_t* __restrict__ masks, uint16_t* __restrict__ bitmaps,
+                     const int numFrames, const int cpr, const int rows)
+{
+  oo_bitmap_lut_body<SKEW>(g, frames, table, masks, bitmaps, numFrames, cpr, rows, nullptr, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// frames under several ranges (object sensor instances gathered into one batch, each carrying its own range): the persistent
+// CTAs dealt out to the ranges as in wo_lut_sets_kernel
+template <bool SKEW>
+__global__ void __launch_bounds__(768, 1)
+oo_bitmap_lut_sets_kernel(const Geometry g, const uint8_t* __restrict__ frames, uint16_t* __restrict__ bitmaps,
+                          const int cpr, const int rows, const int* __restrict__ frameList, const LutSets sets)
+{
+  int k = 0;
+  while (k + 1 < sets.numSets && (int)blockIdx.x >= sets.ctaStart[k + 1])
+    ++k;
+  oo_bitmap_lut_body<SKEW>(g, frames, sets.table[k], sets.masks[k], bitmaps, sets.count[k], cpr, rows,
+                           frameList + sets.listOffset[k], (int)blockIdx.x - sets.ctaStart[k],
+                           sets.ctaStart[k + 1] - sets.ctaStart[k]);
+}
+
+cudaError_t launch_oo_bitmap_lut_sets(const Geometry& g, const uint8_t* frames, uint16_t* bitmaps, int smCount,
+                                      cudaStream_t stream, const int* frameList, LutSets sets)
+{
+  if (sets.numSets <= 0 || sets.numSets > LUT_MAX_SETS || !frameList)
+    return cudaErrorInvalidValue;
+  const int cpr = g.width / 16;
+  if (cpr <= 0 || cpr > 768)
+    return cudaErrorInvalidValue;
+  const int rows = 768 / cpr;
+  const int threads = ((cpr * rows + 31) / 32) * 32;
+  long long total = 0;
+  for (int k = 0; k < sets.numSets; ++k) total += sets.count[k];
+  if (total <= 0)
+    return cudaSuccess;
+  sets.ctaStart[0] = 0;
+  int used = 0, biggest = 0, ctas[LUT_MAX_SETS];
+  for (int k = 0; k < sets.numSets; ++k)
+  {
+    ctas[k] = (int)((long long)smCount * sets.count[k] / total);
+    if (ctas[k] < 1) ctas[k] = 1;
+    used += ctas[k];
+    if (sets.count[k] > sets.count[biggest]) biggest = k;
+  }
+  if (used < smCount)
+    ctas[biggest] += smCount - used;
+  for (int k = 0; k < sets.numSets; ++k)
+  {
+    const long long need = ((long long)sets.count[k] * (g.height / 4) + rows - 1) / rows;
+    if (ctas[k] > need) ctas[k] = (int)need;
+    sets.ctaStart[k + 1] = sets.ctaStart[k] + ctas[k];
+  }
+  const int grid = sets.ctaStart[sets.numSets];
+  const bool skew = g_lutSkew != 0;
+  const int smem = (int)(2u * (skew ? LUT_STRIDE_SKEW : LUT_STRIDE_PLAIN));
+  cudaError_t e = skew ? cudaFuncSetAttribute(oo_bitmap_lut_sets_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                       : cudaFuncSetAttribute(oo_bitmap_lut_sets_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess)
+    return e;
+  if (skew)
+    oo_bitmap_lut_sets_kernel<true><<<grid, threads, smem, stream>>>(g, frames, bitmaps, cpr, rows, frameList, sets);
+  else
+    oo_bitmap_lut_sets_kernel<false><<<grid, threads, smem, stream>>>(g, frames, bitmaps, cpr, rows, frameList, sets);
+  ++g_launches_lut;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_oo_bitmap_lut(const Geometry& g, int numFrames, const uint8_t* frames, const uint8_t* table,
