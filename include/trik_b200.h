@@ -358,6 +358,9 @@ void trikb200_setLutParts(XDAS_Int32 parts);
  * many MiB (so that the overlay kernel's scattered two-byte stores land on lines still in L2); measured slower than the whole
  * batch at once at every size tried, hence 0 (= the whole batch at once) is the default */
 void trikb200_setPreviewChunkMB(XDAS_Int32 mb);
+/* tuning knob: 1 (default) = the line sensors' overlays on a 1:1 preview are full-sector read-modify-writes (one thread per
+ * 32-byte sector a line crosses), 0 = the generic overlay kernel's two-byte stores */
+void trikb200_setPreviewSectorOverlay(XDAS_Int32 on);
 /* tuning knob: edge-line kernel, 0 = packed four-pixels-per-thread form (default, needs 4-byte aligned rows), 1 = one thread
  * per column (first version) */
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant);

@@ -1934,6 +1934,7 @@ void trikb200_setGatherMode(XDAS_Int32 mode) { g_gatherMode = mode; }
 void trikb200_setLutSkew(XDAS_Int32 on) { set_lut_skew(on); }
 void trikb200_setLutParts(XDAS_Int32 parts) { set_lut_parts(parts); }
 void trikb200_setPreviewChunkMB(XDAS_Int32 mb) { set_preview_chunk_bytes((long long)mb << 20); }
+void trikb200_setPreviewSectorOverlay(XDAS_Int32 on) { set_preview_sector_overlay(on); }
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant) { set_edge_variant(variant); }
 void trikb200_setMxnTableThreads(XDAS_Int32 threads) { set_om_table_threads(threads); }
 void trikb200_setZeroCopyBytes(XDAS_Int32 bytes) { g_zeroCopyBytes = bytes; }

@@ -124,6 +124,7 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
                           SumAcc* acc = nullptr, const int* frameList = nullptr);   // frameList: numFrames frame indices
 void set_lut_parts(int parts);
 void set_preview_chunk_bytes(long long bytes);
+void set_preview_sector_overlay(int on);
 // the same for a batch under several threshold sets, in one launch: set k has count[k] frames, their indices at
 // frameList + listOffset[k], its FrameParams at params[paramIndex[k]] and its table / masks; the launcher fills the rest
 constexpr int LUT_MAX_SETS = 8;

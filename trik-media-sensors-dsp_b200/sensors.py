@@ -57,6 +57,7 @@ def lib():
         l.trikb200_setLutSkew.argtypes = [C.c_int32]
         l.trikb200_setLutParts.argtypes = [C.c_int32]
         l.trikb200_setPreviewChunkMB.argtypes = [C.c_int32]
+        l.trikb200_setPreviewSectorOverlay.argtypes = [C.c_int32]
         l.trikb200_setEdgeLineVariant.argtypes = [C.c_int32]
         l.trikb200_setMxnTableThreads.argtypes = [C.c_int32]
         l.trikb200_setZeroCopyBytes.argtypes = [C.c_int32]
