@@ -177,6 +177,14 @@ def cpu_frames_per_sec(cores, frames_per_core, reps=1):
     return total / slowest, total, res[0][2], wall
 
 
+def bench_config(n, world):
+    """the `config` object of the JSON line: the same for both arms (the reference arm times the same workload on the host)"""
+    fbytes = W * H * 2
+    return {"workload": WORKLOAD, "sensor": KIND, "width": W, "height": H, "batch_per_gpu": n, "in_args": list(IN_ARGS),
+            "l2": "inputs (%.0f MB per GPU) larger than L2, no flush" % (n * fbytes / 1e6),
+            "parallelism": "frames sharded by batch across %d GPU(s), no data-path collective" % world}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -201,7 +209,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int16 lanes", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sensor": KIND, "width": W, "height": H, "batch_per_gpu": BATCH},
+        "config": bench_config(BATCH, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if is_ref else "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
@@ -597,9 +605,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int16 lanes", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sensor": KIND, "width": W, "height": H, "batch_per_gpu": n,
-                       "in_args": list(IN_ARGS), "l2": "inputs (%.0f MB per GPU) larger than L2, no flush" % (n * fbytes / 1e6),
-                       "parallelism": "frames sharded by batch across %d GPU(s), no data-path collective" % world},
+            "config": bench_config(n, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic if n == BATCH else None, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernel": "vsum_kernel<YUYV> (WL)",
@@ -617,7 +623,7 @@ def main():
             "sustained": sustained,
             "config4_mixed_streams": mixed,
         }
-        line["config"]["host_affinity"] = ("rank bound to its GPU's NUMA node: %d of %d CPUs" % (len(bound[1]), len(bound[0]))
+        line["host_affinity"] = ("rank bound to its GPU's NUMA node: %d of %d CPUs" % (len(bound[1]), len(bound[0]))
                                            if bound else "unbound (NVML affinity query unavailable)")
         if not args.no_others and world == 1:
             extras(line, args, torch, dev, stream, sptr, timed, peak, sampler_factory=lambda: ClockSampler(local_rank))
