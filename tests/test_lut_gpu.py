@@ -200,3 +200,38 @@ def test_oo_batch_under_several_ranges_takes_the_tables():
             assert ok == 1 and bytes(memoryview(got[i]))[:24] == bytes(memoryview(exp))[:24], i
     for c in (codec, codec2, codec3):
         c.close()
+
+
+@pytest.mark.parametrize("size", [(320, 240), (640, 480), (160, 120)])
+def test_bands_of_rows_give_the_same_records(size):
+    """the table kernel's work items are whole frames or 2 / 4 / 8 bands of rows meeting in the frame's accumulator record
+    (chosen per launch; forced here): the records must not depend on it -- one threshold set and several"""
+    w, h = size
+    n = 330
+    frames = synth.make_batch("scene", range(n), w, h, "yuyv")
+    one = xdm.RangeInArgsAlg(*THRESHOLDS[0])
+    many = (xdm.RangeInArgsAlg * n)(*[xdm.RangeInArgsAlg(*THRESHOLDS[(0, 1, 4)[i % 3]]) for i in range(n)])
+    L = lib()
+    L.trikb200_setLutMode(1)
+    results = {}
+    try:
+        for parts in (1, 2, 4, 8, 0):
+            L.trikb200_setLutParts(parts)
+            codec = open_sensor("wo", w, h)
+            for name, ia in (("one", one), ("many", many)):
+                for rep in range(2):                              # twice: the accumulator records must be back at zero
+                    ret, outs = codec.process_batch(frames, ia)
+                    assert ret == 0, L.trikb200_lastError()
+                    results[(parts, name, rep)] = [bytes(memoryview(o))[:3] for o in outs]
+            codec.close()
+    finally:
+        L.trikb200_setLutParts(0)
+    for name in ("one", "many"):
+        want = results[(1, name, 0)]
+        for parts in (1, 2, 4, 8, 0):
+            for rep in range(2):
+                assert results[(parts, name, rep)] == want, (size, parts, name, rep)
+    orc = oracle.OracleSensor("wo", w, h)
+    for i in range(0, n, 11):
+        ok, exp = orc.process(frames[i], oracle.RangeInArgs(*THRESHOLDS[0]))
+        assert ok == 1 and results[(1, "one", 0)][i] == bytes(memoryview(exp))[:3], i

@@ -586,13 +586,17 @@ static int lut_bands(int numFrames, long long slots, int height, int rpi, int st
   int parts = 1;
   if (g_lutParts == 1)
     return 1;
+  if (g_lutParts > 1)                       // forced (measurements, tests): as asked, down to one row iteration per band
+  {
+    int forced = g_lutParts > 8 ? 8 : g_lutParts;
+    while (forced > 1 && height / forced < rpi) forced >>= 1;
+    return forced;
+  }
   double best = 0.0;
   for (int cand = 1; cand <= 8; cand *= 2)
   {
     if (cand > 1 && height / cand < rpi * 2 * stages)
       break;
-    if (g_lutParts > 1 && cand != g_lutParts)
-      continue;
     const long long items = (long long)numFrames * cand;
     const double eff = items <= slots ? 1.0 : (double)items / slots / (double)((items + slots - 1) / slots);
     if (eff > best + 1e-9) { best = eff; parts = cand; }
