@@ -117,3 +117,85 @@ def test_one_to_one_batch_previews_in_sub_batches(kind):
         r, oa = codec.process(frames[i], ia)
         assert r == 0 and np.array_equal(codec.preview[:w * h * 2], images[0][i]), (kind, i)
     codec.close()
+
+
+@pytest.mark.parametrize("kind", ["wl", "ol"])
+@pytest.mark.parametrize("size", [(320, 240), (640, 480), (160, 120)])
+def test_line_overlay_modes_give_the_same_previews(kind, size):
+    """line sensors, 1:1 preview: the overlays come from the generic overlay kernel (0), from the full-sector kernel (1) or
+    from the last CTA of each frame inside the streaming kernel (2, CTAs count themselves in at the frame's DrawInfo record):
+    every byte the same, on a second batch too (the counters must be back at zero), and equal to single process() calls,
+    which test_preview_matches_reference pins to the reference's own drawing"""
+    w, h = size
+    n = 37
+    layout = sensors.layout_of(xdm.KIND_OF[kind])
+    fams = ["scene", "halves", "noise", "bluewrap"]
+    frames = np.stack([synth.make_frame(fams[s % 4], s, w, h, layout) for s in range(n)])
+    ia = xdm.IN_ARGS_ALG[xdm.KIND_OF[kind]](*args_for(kind, 0))
+    L = sensors.lib()
+    images = {}
+    try:
+        for mode in (0, 1, 2, 4, -1):
+            L.trikb200_setPreviewSectorOverlay(mode)
+            codec = open_sensor(kind, w, h, out_w=w, out_h=h)
+            for rep in range(2):
+                prev = np.full((n, w * h * 2), 0xAB, dtype=np.uint8)
+                ret, outs = codec.process_batch(frames, ia, previews=prev)
+                assert ret == 0, sensors.last_error()
+                images[(mode, rep)] = (prev, [bytes(memoryview(o)) for o in outs])
+            codec.close()
+    finally:
+        L.trikb200_setPreviewSectorOverlay(-1)
+    # OL carries state from frame to frame, so compare rep 0 with rep 0 and rep 1 with rep 1 across the modes
+    for rep in range(2):
+        for mode in (1, 2, 4, -1):
+            assert images[(mode, rep)][1] == images[(0, rep)][1], (kind, size, mode, rep)
+            assert np.array_equal(images[(mode, rep)][0], images[(0, rep)][0]), (kind, size, mode, rep)
+    try:
+        L.trikb200_setPreviewSectorOverlay(2)
+        codec = open_sensor(kind, w, h, out_w=w, out_h=h)
+        for i in range(n):
+            r, oa = codec.process(frames[i], ia)
+            assert r == 0 and np.array_equal(codec.preview[:w * h * 2], images[(0, 0)][0][i]), (kind, size, i)
+        codec.close()
+    finally:
+        L.trikb200_setPreviewSectorOverlay(-1)
+
+
+@pytest.mark.parametrize("kind", ["wl", "ol"])
+def test_long_preview_pass_default_route(kind):
+    """a pass over >= 384 MiB of 1:1 previews takes the fused route by default (overlays by the last CTA of each frame inside
+    the streaming kernel): 700 device-resident 640x480 frames, every preview byte and every record equal to the route through
+    the separate sector kernel, twice (the arrival counters must be back at zero); one launch fewer per batch"""
+    import torch
+    from trik_media_sensors_dsp_b200 import launch_count
+    w, h, n, uniq = 640, 480, 700, 20
+    layout = sensors.layout_of(xdm.KIND_OF[kind])
+    fams = ["scene", "halves", "noise", "bluewrap"]
+    base = np.stack([synth.make_frame(fams[s % 4], s, w, h, layout) for s in range(uniq)])
+    dev = torch.device("cuda", 0)
+    d_frames = torch.from_numpy(base).to(dev).repeat((n + uniq - 1) // uniq, 1)[:n].contiguous()
+    fbytes = base.shape[1]
+    ia = xdm.IN_ARGS_ALG[xdm.KIND_OF[kind]](*args_for(kind, 0))
+    L = sensors.lib()
+    got = {}
+    try:
+        for mode in (1, -1):
+            L.trikb200_setPreviewSectorOverlay(mode)
+            codec = open_sensor(kind, w, h, out_w=w, out_h=h)
+            for rep in range(2):
+                d_prev = torch.full((n, w * h * 2), 0xAB, dtype=torch.uint8, device=dev)
+                torch.cuda.synchronize()
+                before = launch_count()
+                ret, outs = codec.process_batch(d_frames.data_ptr(), ia, frames_device=True, frame_stride=fbytes, num_frames=n,
+                                                previews_device_ptr=d_prev.data_ptr(), preview_stride=w * h * 2)
+                assert ret == 0, sensors.last_error()
+                torch.cuda.synchronize()
+                got[(mode, rep)] = (d_prev, [bytes(memoryview(o)) for o in outs], launch_count() - before)
+            codec.close()
+    finally:
+        L.trikb200_setPreviewSectorOverlay(-1)
+    for rep in range(2):
+        assert got[(-1, rep)][1] == got[(1, rep)][1], (kind, rep)
+        assert torch.equal(got[(-1, rep)][0], got[(1, rep)][0]), (kind, rep)
+        assert got[(-1, rep)][2] == got[(1, rep)][2] - 1, (kind, rep, got[(-1, rep)][2], got[(1, rep)][2])

@@ -35,7 +35,7 @@ def main():
     sensors.lib().trikb200_setMxnTableThreads(int(os.environ.get("OMTHREADS", "0")))
     sensors.lib().trikb200_setLutSkew(int(os.environ.get("SKEW", "1")))
     sensors.lib().trikb200_setPreviewChunkMB(int(os.environ.get("PVCHUNK", "0")))   # MiB of preview images per sub-batch, 0 = all at once
-    sensors.lib().trikb200_setPreviewSectorOverlay(int(os.environ.get("PVSECTOR", "1")))   # 0: generic overlay kernel for the line sensors
+    sensors.lib().trikb200_setPreviewSectorOverlay(int(os.environ.get("PVSECTOR", "-1")))   # -1: fused into the streaming kernel (default), 0: generic overlay kernel, 1: sector kernel
     sensors.lib().trikb200_setLutParts(int(os.environ.get("LUTPARTS", "0")))        # bands per frame of the WO table kernel
     sensors.lib().trikb200_setOverlapLaunch(int(os.environ.get("OVERLAP", "1")))   # 0: no programmatic dependent launches
     peak = 6541.1

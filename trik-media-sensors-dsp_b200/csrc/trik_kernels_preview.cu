@@ -25,7 +25,9 @@ extern std::atomic<long long> g_launches_preview;
 std::atomic<long long> g_launches_preview{0};
 static long long g_previewChunkBytes = 0;                // images of one sub-batch of a 1:1 preview pass (0 = whole batch at once, the default)
 void set_preview_chunk_bytes(long long bytes) { g_previewChunkBytes = bytes; }
-static int g_sectorOverlay = 1;                          // line sensors, 1:1 preview: overlays as full-sector read-modify-writes
+static int g_sectorOverlay = -1;                         // line sensors, 1:1 preview: -1 = overlays by the last CTA of each frame inside the
+                                                         // streaming kernel for long passes, else the full-sector kernel (default), 0 = generic
+                                                         // overlay kernel, 1 = full-sector kernel always, >= 2 = fused always, forced blocks per CTA
 void set_preview_sector_overlay(int on) { g_sectorOverlay = on; }
 
 __device__ __forceinline__ uint16_t rgb565x(uint32_t rgb888)           // writeOutputPixel (:66-70)
@@ -137,11 +139,18 @@ __device__ __forceinline__ uint32_t rgb565x_pair(uint32_t r2, uint32_t g2, uint3
 }
 
 template <int KIND>
+__device__ __forceinline__ void lines_sector_item(const Geometry& g, const int2 d, const int outLine, uint8_t* img, const int item);
+
+// FUSE (line sensors, trikb200_setPreviewSectorOverlay(2)): the CTAs of a frame count themselves in at the frame's DrawInfo
+// record (v[19], back at zero afterwards) and the last one to arrive draws the frame's line overlays as the same full-sector
+// read-modify-writes as preview_lines_sector_kernel -- on lines the frame's CTAs have just written, i.e. still in L2 (no
+// sector fill from DRAM, one write-back per line), and without a second launch.
+template <int KIND, bool FUSE>
 __global__ void __launch_bounds__(256)
 preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
                         const int paramStride, const uint16_t* __restrict__ bitmaps, const int outLine,
                         uint8_t* __restrict__ previews, const long long previewStride, const int numFrames,
-                        const uint32_t cprMagic, const int colFirst, const int colLast)
+                        const uint32_t cprMagic, const int colFirst, const int colLast, DrawInfo* draw, const int iters)
 {
   constexpr bool PLANAR = (KIND == KIND_OO || KIND == KIND_OL || KIND == KIND_OM);
   __shared__ uint16_t s_lut43[256];
@@ -153,14 +162,26 @@ preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, co
     fill_hue_lut(s_lutHue);
     __syncthreads();
   }
+  __shared__ int s_last;
   const int cpr = g.width >> 3;
-  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= (uint32_t)cpr * (uint32_t)g.height)
+  const uint32_t item0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!FUSE && item0 >= (uint32_t)cpr * (uint32_t)g.height)
     return;
-  const int row = (int)__umulhi(item, cprMagic), c = (int)item - row * cpr;
-  const int col0 = c * 8;
+  const int row0 = (int)__umulhi(item0, cprMagic), cc0 = (int)item0 - row0 * cpr;
   for (int frame = blockIdx.y; frame < numFrames; frame += gridDim.y)
   {
+    // FUSE: a CTA takes `iters` consecutive blocks of 256 items, so that the counting-in below is paid once per several rows
+    for (int it = 0; it < (FUSE ? iters : 1); ++it)
+    {
+    int row = row0, c = cc0;
+    if (FUSE)
+    {
+      const uint32_t item = (blockIdx.x * (uint32_t)iters + (uint32_t)it) * blockDim.x + threadIdx.x;
+      if (item >= (uint32_t)cpr * (uint32_t)g.height)
+        break;
+      row = (int)__umulhi(item, cprMagic); c = (int)item - row * cpr;
+    }
+    const int col0 = c * 8;
     const uint8_t* fr = frames + (size_t)frame * g.frameStride;
     uint32_t yy[4], cw[4];
     if (!PLANAR)
@@ -246,6 +267,31 @@ preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, co
     }
     *reinterpret_cast<uint4*>(previews + (size_t)frame * previewStride + (size_t)row * outLine + (size_t)c * 16)
         = make_uint4(px[0], px[1], px[2], px[3]);
+    }
+    if (FUSE)
+    {
+      // the CTA's pixels, then (barrier, cumulative fence of one thread: the grid-barrier idiom) its count
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+        __threadfence();
+        const uint32_t before = atomicAdd(reinterpret_cast<uint32_t*>(&draw[frame].v[19]), 1u);
+        s_last = before == gridDim.x - 1u;
+      }
+      __syncthreads();
+      if (s_last)
+      {
+        __threadfence();
+        const int2 d = __ldcg(reinterpret_cast<const int2*>(draw[frame].v));
+        const int items = g.height * 6 + (KIND == KIND_OL ? 2 * (g.width >> 4) : 0);
+        uint8_t* img = previews + (size_t)frame * previewStride;
+        for (int it = (int)threadIdx.x; it < items; it += (int)blockDim.x)
+          lines_sector_item<KIND>(g, make_int2(d.x, d.y), outLine, img, it);
+        if (threadIdx.x == 0)
+          draw[frame].v[19] = 0;
+      }
+      __syncthreads();                                           // s_last is rewritten by the next frame of this CTA
+    }
   }
 }
 
@@ -381,71 +427,78 @@ preview_overlay_kernel(const Geometry g, const FrameParams* __restrict__ params,
 // the ov7670 sensor 2 rows x W/16 sectors.
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(128)
-preview_lines_sector_kernel(const Geometry g, const DrawInfo* __restrict__ draw, const int outLine,
-                            uint8_t* __restrict__ previews, const long long previewStride, const int numFrames)
+__device__ __forceinline__ void lines_sector_item(const Geometry& g, const int2 d, const int outLine, uint8_t* img, const int item)
 {
   const int W = g.width, H = g.height, hW = W >> 1, hH = H >> 1, spr = W >> 4;
   auto clampc = [&](int x) { return x < 0 ? 0 : (x > W - 1 ? W - 1 : x); };
   auto clampr = [&](int y) { return y < 0 ? 0 : (y > H - 1 ? H - 1 : y); };
   const int c0 = clampc(hW - 80), c1 = clampc(hW - 40), c2 = clampc(hW + 40), c3 = clampc(hW + 80);   // WL :384-387
   const int rA = clampr(hH), rB = clampr(hH + 80);                                                    // OL :454-455
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
   constexpr uint32_t MAGENTA = 0xF81Fu, RED = 0x001Fu;             // rgb565x(0xFF00FF), rgb565x(0xFF0000)
+  // d: points > 10, target column (WL :410)
+  const int L = clampc(d.y - 1), R = clampc(d.y + 1);
+  int row, sec;
+  bool wholeRow = false;
+  if (item < H * 6)
+  {
+    row = item / 6;
+    const int sIdx = item - row * 6;
+    const int cand[6] = {c0 >> 4, c1 >> 4, c2 >> 4, c3 >> 4, d.x ? L >> 4 : -1, d.x ? R >> 4 : -1};
+    sec = -1;
+    bool dup = false;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+    {
+      if (j == sIdx) sec = cand[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      if (j < sIdx && cand[j] == sec) dup = true;
+    if (sec < 0 || dup)
+      return;
+    if (KIND == KIND_OL && (row == rA || row == rB))
+      return;                                                    // the whole row is somebody else's
+  }
+  else if (KIND == KIND_OL && item < H * 6 + 2 * spr)
+  {
+    const int idx = item - H * 6;
+    const int which = idx >= spr ? 1 : 0;
+    if (which == 1 && rB == rA)
+      return;
+    row = which ? rB : rA;
+    sec = idx - which * spr;
+    wholeRow = true;
+  }
+  else
+    return;
+  uint4* const p = reinterpret_cast<uint4*>(img + (size_t)row * outLine + (size_t)sec * 32);
+  const uint4 a = __ldcg(p), b = __ldcg(p + 1);                  // L2: the fused caller reads what other SMs have just written
+  uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+  {
+    const int col = sec * 16 + k;
+    int colour = -1;
+    if (col == c0 || col == c1 || col == c2 || col == c3) colour = (int)MAGENTA;
+    if (wholeRow) colour = (int)RED;
+    if (d.x && col >= L && col <= R) colour = (int)RED;
+    if (colour >= 0)
+      w[k >> 1] = (k & 1) ? (w[k >> 1] & 0x0000FFFFu) | ((uint32_t)colour << 16) : (w[k >> 1] & 0xFFFF0000u) | (uint32_t)colour;
+  }
+  p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128)
+preview_lines_sector_kernel(const Geometry g, const DrawInfo* __restrict__ draw, const int outLine,
+                            uint8_t* __restrict__ previews, const long long previewStride, const int numFrames)
+{
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
   for (int frame = blockIdx.y; frame < numFrames; frame += gridDim.y)
   {
-    const int2 d = *reinterpret_cast<const int2*>(draw[frame].v);  // points > 10, target column (WL :410)
-    const int L = clampc(d.y - 1), R = clampc(d.y + 1);
-    int row, sec;
-    bool wholeRow = false;
-    if (item < H * 6)
-    {
-      row = item / 6;
-      const int sIdx = item - row * 6;
-      const int cand[6] = {c0 >> 4, c1 >> 4, c2 >> 4, c3 >> 4, d.x ? L >> 4 : -1, d.x ? R >> 4 : -1};
-      sec = -1;
-      bool dup = false;
-#pragma unroll
-      for (int j = 0; j < 6; ++j)
-      {
-        if (j == sIdx) sec = cand[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 6; ++j)
-        if (j < sIdx && cand[j] == sec) dup = true;
-      if (sec < 0 || dup)
-        continue;
-      if (KIND == KIND_OL && (row == rA || row == rB))
-        continue;                                                  // the whole row is somebody else's
-    }
-    else if (KIND == KIND_OL && item < H * 6 + 2 * spr)
-    {
-      const int idx = item - H * 6;
-      const int which = idx >= spr ? 1 : 0;
-      if (which == 1 && rB == rA)
-        continue;
-      row = which ? rB : rA;
-      sec = idx - which * spr;
-      wholeRow = true;
-    }
-    else
-      continue;
-    uint4* const p = reinterpret_cast<uint4*>(previews + (size_t)frame * previewStride + (size_t)row * outLine + (size_t)sec * 32);
-    const uint4 a = p[0], b = p[1];
-    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-    {
-      const int col = sec * 16 + k;
-      int colour = -1;
-      if (col == c0 || col == c1 || col == c2 || col == c3) colour = (int)MAGENTA;
-      if (wholeRow) colour = (int)RED;
-      if (d.x && col >= L && col <= R) colour = (int)RED;
-      if (colour >= 0)
-        w[k >> 1] = (k & 1) ? (w[k >> 1] & 0x0000FFFFu) | ((uint32_t)colour << 16) : (w[k >> 1] & 0xFFFF0000u) | (uint32_t)colour;
-    }
-    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    const int2 d = *reinterpret_cast<const int2*>(draw[frame].v);
+    lines_sector_item<KIND>(g, d, outLine, previews + (size_t)frame * previewStride, item);
   }
 }
 
@@ -492,6 +545,23 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
     {
       const int cnt = numFrames - f0 < chunk ? numFrames - f0 : chunk;
       const dim3 cgrid(igrid.x, (unsigned)(cnt < 65535 ? cnt : 65535));
+      // fused overlays count CTAs in per frame: every frame must be visited by exactly gridDim.x CTAs (it is: the frame
+      // loop strides by gridDim.y for all of them alike) and the frame's record must exist
+      // By default only for long passes (>= 384 MiB of images): the last CTA of a frame walks the frame's ~H * 6 sectors in
+      // H * 6 / 256 dependent rounds, which a short pass cannot hide -- 64 x 320x240: 0.034 ms fused against 0.018 ms with the
+      // sector kernel, 1024 x 320x240 0.132 against 0.130 ms, 4096 x 320x240 0.435 against 0.475 ms, 1024 x 640x480 0.440
+      // against 0.477 ms (profiles/r02w_*, r02x_*).
+      const bool longPass = (unsigned long long)cnt * perFrame >= (384ull << 20);
+      const bool fused = ((g_sectorOverlay < 0 && longPass) || g_sectorOverlay >= 2) && draw != nullptr && (kind == KIND_WL || kind == KIND_OL);
+      // blocks of 256 items per CTA: forced (2: 1, 3: 2, 4: 4, 5: 8 ...) or, by default, as many as leave about four waves of
+      // CTAs, at most 16 -- measured on 1024 x 640x480 WL (profiles/r02w_*): 1 / 2 / 4 / 8 / 16 / 32 / 64 blocks per CTA
+      // 0.564 / 0.490 / 0.466 / 0.449 / 0.438 / 0.447 / 0.464 ms against 0.476 ms with the separate sector kernel
+      unsigned fuseIters = 1u;
+      if (g_sectorOverlay >= 2)
+        fuseIters = 1u << (g_sectorOverlay <= 8 ? g_sectorOverlay - 2 : 6);
+      else
+        while (fuseIters < 16u && (unsigned long long)cgrid.x * cgrid.y / (fuseIters * 2u) >= 4ull * 148ull * 8ull)
+          fuseIters *= 2u;
       const uint8_t* cf = frames + (size_t)f0 * g.frameStride;
       const FrameParams* cp = params + (size_t)f0 * paramStride;
       const uint16_t* cb = bitmaps ? bitmaps + (size_t)f0 * cells : nullptr;
@@ -499,23 +569,28 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
       const int32_t* co = omColours ? omColours + (size_t)f0 * 100 : nullptr;
       uint8_t* cpv = previews + (size_t)f0 * previewStride;
 #define TRIK_PREVIEW_ID(K)                                                                                         \
-  preview_identity_kernel<K><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,                      \
-                                                        previewStride, cnt, cprMagic, colFirst, colLast);              \
+  preview_identity_kernel<K, false><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,               \
+                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1);     \
   preview_overlay_kernel<K><<<(unsigned)cnt, OVERLAY_THREADS, 0, stream>>>(g, cp, paramStride, cd, co, pg, cpv, previewStride)
 #define TRIK_PREVIEW_LINES(K)                                                                                      \
-  preview_identity_kernel<K><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,                      \
-                                                        previewStride, cnt, cprMagic, colFirst, colLast);              \
+  preview_identity_kernel<K, false><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,               \
+                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1);     \
   preview_lines_sector_kernel<K><<<dim3((unsigned)((g.height * 6 + 2 * (g.width >> 4) + 127) / 128), cgrid.y), 128, 0, stream>>>( \
       g, cd, outLine, cpv, previewStride, cnt)
+#define TRIK_PREVIEW_FUSED(K)                                                                                      \
+  preview_identity_kernel<K, true><<<dim3((cgrid.x + fuseIters - 1) / fuseIters, cgrid.y), 256, 0, stream>>>(          \
+      g, cf, cp, paramStride, cb, outLine, cpv, previewStride, cnt, cprMagic, colFirst, colLast, const_cast<DrawInfo*>(cd), (int)fuseIters); \
+  --g_launches_preview
       switch (kind)
       {
         case KIND_WO: TRIK_PREVIEW_ID(KIND_WO); break;
-        case KIND_WL: if (g_sectorOverlay) { TRIK_PREVIEW_LINES(KIND_WL); } else { TRIK_PREVIEW_ID(KIND_WL); } break;
+        case KIND_WL: if (fused) { TRIK_PREVIEW_FUSED(KIND_WL); } else if (g_sectorOverlay) { TRIK_PREVIEW_LINES(KIND_WL); } else { TRIK_PREVIEW_ID(KIND_WL); } break;
         case KIND_OO: TRIK_PREVIEW_ID(KIND_OO); break;
-        case KIND_OL: if (g_sectorOverlay) { TRIK_PREVIEW_LINES(KIND_OL); } else { TRIK_PREVIEW_ID(KIND_OL); } break;
+        case KIND_OL: if (fused) { TRIK_PREVIEW_FUSED(KIND_OL); } else if (g_sectorOverlay) { TRIK_PREVIEW_LINES(KIND_OL); } else { TRIK_PREVIEW_ID(KIND_OL); } break;
         case KIND_OM: TRIK_PREVIEW_ID(KIND_OM); break;
         default: return cudaErrorInvalidValue;
       }
+#undef TRIK_PREVIEW_FUSED
 #undef TRIK_PREVIEW_LINES
 #undef TRIK_PREVIEW_ID
       g_launches_preview += 2;
