@@ -358,11 +358,12 @@ void trikb200_setLutParts(XDAS_Int32 parts);
  * many MiB (so that the overlay kernel's scattered two-byte stores land on lines still in L2); measured slower than the whole
  * batch at once at every size tried, hence 0 (= the whole batch at once) is the default */
 void trikb200_setPreviewChunkMB(XDAS_Int32 mb);
-/* tuning knob, line sensors' overlays on a 1:1 preview: -1 (default) = for passes over >= 384 MiB of images drawn by the
- * last CTA of each frame inside the streaming preview kernel, as full-sector read-modify-writes on lines still in L2 (no
- * second launch), else as under 1; 1 = the same read-modify-writes as a kernel of their own (one thread per 32-byte sector
- * a line crosses); 0 = the generic overlay kernel's two-byte stores; 2..8 = fused always, with a forced 1, 2, 4 .. 64 blocks
- * of 256 items per CTA (measurements, tests) */
+/* tuning knob, where the line sensors' overlays on a 1:1 preview are drawn: -1 (default) = inside the streaming preview
+ * kernel, every CTA patching the 32-byte sectors the lines cross among the rows it has just written (still in L2, no second
+ * launch); 1 = the same full-sector read-modify-writes as a kernel of their own; 0 = the generic overlay kernel's two-byte
+ * stores; 2..8 = inside, by the last CTA of each frame to arrive (1, 2 .. 64 blocks of 256 items per CTA); 9..15 = inside,
+ * CTA-local with a forced 1, 2 .. 64 blocks per CTA.  All byte-identical (tests/test_preview_gpu.py); measurements in
+ * DESIGN.md 3.7 */
 void trikb200_setPreviewSectorOverlay(XDAS_Int32 on);
 /* tuning knob: edge-line kernel, 0 = packed four-pixels-per-thread form (default, needs 4-byte aligned rows), 1 = one thread
  * per column (first version) */

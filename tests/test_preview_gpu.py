@@ -122,10 +122,11 @@ def test_one_to_one_batch_previews_in_sub_batches(kind):
 @pytest.mark.parametrize("kind", ["wl", "ol"])
 @pytest.mark.parametrize("size", [(320, 240), (640, 480), (160, 120)])
 def test_line_overlay_modes_give_the_same_previews(kind, size):
-    """line sensors, 1:1 preview: the overlays come from the generic overlay kernel (0), from the full-sector kernel (1) or
-    from the last CTA of each frame inside the streaming kernel (2, CTAs count themselves in at the frame's DrawInfo record):
-    every byte the same, on a second batch too (the counters must be back at zero), and equal to single process() calls,
-    which test_preview_matches_reference pins to the reference's own drawing"""
+    """line sensors, 1:1 preview: the overlays come from the generic overlay kernel (0), from the full-sector kernel (1), from
+    the last CTA of each frame inside the streaming kernel (2, 4: CTAs count themselves in at the frame's DrawInfo record) or
+    from every CTA for its own rows (9, 12, and -1 = the default): every byte the same, on a second batch too (the counters
+    must be back at zero), and equal to single process() calls, which test_preview_matches_reference pins to the reference's
+    own drawing"""
     w, h = size
     n = 37
     layout = sensors.layout_of(xdm.KIND_OF[kind])
@@ -135,7 +136,7 @@ def test_line_overlay_modes_give_the_same_previews(kind, size):
     L = sensors.lib()
     images = {}
     try:
-        for mode in (0, 1, 2, 4, -1):
+        for mode in (0, 1, 2, 4, 9, 12, -1):
             L.trikb200_setPreviewSectorOverlay(mode)
             codec = open_sensor(kind, w, h, out_w=w, out_h=h)
             for rep in range(2):
@@ -148,7 +149,7 @@ def test_line_overlay_modes_give_the_same_previews(kind, size):
         L.trikb200_setPreviewSectorOverlay(-1)
     # OL carries state from frame to frame, so compare rep 0 with rep 0 and rep 1 with rep 1 across the modes
     for rep in range(2):
-        for mode in (1, 2, 4, -1):
+        for mode in (1, 2, 4, 9, 12, -1):
             assert images[(mode, rep)][1] == images[(0, rep)][1], (kind, size, mode, rep)
             assert np.array_equal(images[(mode, rep)][0], images[(0, rep)][0]), (kind, size, mode, rep)
     try:
@@ -164,9 +165,8 @@ def test_line_overlay_modes_give_the_same_previews(kind, size):
 
 @pytest.mark.parametrize("kind", ["wl", "ol"])
 def test_long_preview_pass_default_route(kind):
-    """a pass over >= 384 MiB of 1:1 previews takes the fused route by default (overlays by the last CTA of each frame inside
-    the streaming kernel): 700 device-resident 640x480 frames, every preview byte and every record equal to the route through
-    the separate sector kernel, twice (the arrival counters must be back at zero); one launch fewer per batch"""
+    """a long pass of 1:1 previews (700 device-resident 640x480 frames, eight blocks of 256 items per CTA by the default rule):
+    every preview byte and every record equal to the route through the separate sector kernel, twice; one launch fewer"""
     import torch
     from trik_media_sensors_dsp_b200 import launch_count
     w, h, n, uniq = 640, 480, 700, 20

@@ -25,9 +25,9 @@ extern std::atomic<long long> g_launches_preview;
 std::atomic<long long> g_launches_preview{0};
 static long long g_previewChunkBytes = 0;                // images of one sub-batch of a 1:1 preview pass (0 = whole batch at once, the default)
 void set_preview_chunk_bytes(long long bytes) { g_previewChunkBytes = bytes; }
-static int g_sectorOverlay = -1;                         // line sensors, 1:1 preview: -1 = overlays by the last CTA of each frame inside the
-                                                         // streaming kernel for long passes, else the full-sector kernel (default), 0 = generic
-                                                         // overlay kernel, 1 = full-sector kernel always, >= 2 = fused always, forced blocks per CTA
+static int g_sectorOverlay = -1;                         // line sensors, 1:1 preview, where the overlays are drawn: -1 = inside the streaming
+                                                         // kernel, CTA-local (default); 0 = generic overlay kernel; 1 = full-sector kernel;
+                                                         // 2..8 = inside, counting (forced blocks per CTA); 9..15 = inside, CTA-local (forced)
 void set_preview_sector_overlay(int on) { g_sectorOverlay = on; }
 
 __device__ __forceinline__ uint16_t rgb565x(uint32_t rgb888)           // writeOutputPixel (:66-70)
@@ -139,18 +139,20 @@ __device__ __forceinline__ uint32_t rgb565x_pair(uint32_t r2, uint32_t g2, uint3
 }
 
 template <int KIND>
-__device__ __forceinline__ void lines_sector_item(const Geometry& g, const int2 d, const int outLine, uint8_t* img, const int item);
+__device__ __forceinline__ void lines_sector_item(const Geometry& g, const int2 d, const int outLine, uint8_t* img, const int item,
+                                                  const uint32_t chunkFirst = 0u, const uint32_t chunkEnd = 0xFFFFFFFFu);
 
-// FUSE (line sensors, trikb200_setPreviewSectorOverlay(2)): the CTAs of a frame count themselves in at the frame's DrawInfo
-// record (v[19], back at zero afterwards) and the last one to arrive draws the frame's line overlays as the same full-sector
-// read-modify-writes as preview_lines_sector_kernel -- on lines the frame's CTAs have just written, i.e. still in L2 (no
-// sector fill from DRAM, one write-back per line), and without a second launch.
+// FUSE (line sensors): the frame's line overlays inside this kernel, as the same full-sector read-modify-writes as
+// preview_lines_sector_kernel but on lines that have just been written, i.e. still in L2 (no sector fill from DRAM, one
+// write-back per line), and without a second launch.  Either CTA-local (`local`, the default: every CTA patches its own rows
+// after a barrier) or counting (the CTAs of a frame count themselves in at the frame's DrawInfo record, v[19], back at zero
+// afterwards, and the last one to arrive patches the whole frame).  A CTA takes `iters` blocks of 256 items.
 template <int KIND, bool FUSE>
 __global__ void __launch_bounds__(256)
 preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
                         const int paramStride, const uint16_t* __restrict__ bitmaps, const int outLine,
                         uint8_t* __restrict__ previews, const long long previewStride, const int numFrames,
-                        const uint32_t cprMagic, const int colFirst, const int colLast, DrawInfo* draw, const int iters)
+                        const uint32_t cprMagic, const int colFirst, const int colLast, DrawInfo* draw, const int iters, const int local)
 {
   constexpr bool PLANAR = (KIND == KIND_OO || KIND == KIND_OL || KIND == KIND_OM);
   __shared__ uint16_t s_lut43[256];
@@ -268,7 +270,26 @@ preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, co
     *reinterpret_cast<uint4*>(previews + (size_t)frame * previewStride + (size_t)row * outLine + (size_t)c * 16)
         = make_uint4(px[0], px[1], px[2], px[3]);
     }
-    if (FUSE)
+    if (FUSE && local)
+    {
+      // CTA-local: a 32-byte sector is two consecutive items with an even first index and W/8 is even, so every sector lies
+      // inside ONE CTA's blocks of 256 items: after a barrier the CTA patches the sectors the lines cross among the rows it has
+      // just written itself (its own stores, read back from L2) -- no counting, no fence, nobody waits for anybody
+      __syncthreads();
+      const uint32_t total = (uint32_t)cpr * (uint32_t)g.height;
+      const uint32_t a = blockIdx.x * (uint32_t)iters * blockDim.x, b = min(a + (uint32_t)iters * blockDim.x, total);
+      if (a < b)
+      {
+        const int rowFirst = (int)__umulhi(a, cprMagic), rowLast = (int)__umulhi(b - 1u, cprMagic);
+        const int2 d = __ldcg(reinterpret_cast<const int2*>(draw[frame].v));
+        const int nLocal = (rowLast - rowFirst + 1) * 6;
+        const int nAll = nLocal + (KIND == KIND_OL ? 2 * (g.width >> 4) : 0);
+        uint8_t* img = previews + (size_t)frame * previewStride;
+        for (int t = (int)threadIdx.x; t < nAll; t += (int)blockDim.x)
+          lines_sector_item<KIND>(g, d, outLine, img, t < nLocal ? rowFirst * 6 + t : g.height * 6 + (t - nLocal), a, b);
+      }
+    }
+    else if (FUSE)
     {
       // the CTA's pixels, then (barrier, cumulative fence of one thread: the grid-barrier idiom) its count
       __syncthreads();
@@ -426,8 +447,11 @@ preview_overlay_kernel(const Geometry g, const FrameParams* __restrict__ params,
 // H rows x 6 candidate sectors (four fixed columns, first and last column of the target line; duplicates dropped), plus for
 // the ov7670 sensor 2 rows x W/16 sectors.
 // ---------------------------------------------------------------------------------------------
+// chunkFirst .. chunkEnd: only sectors whose first 16-byte chunk (index row * W/8 + 2 * sector, as the streaming kernel counts
+// its items) lies in this range -- the caller that has just written exactly these chunks
 template <int KIND>
-__device__ __forceinline__ void lines_sector_item(const Geometry& g, const int2 d, const int outLine, uint8_t* img, const int item)
+__device__ __forceinline__ void lines_sector_item(const Geometry& g, const int2 d, const int outLine, uint8_t* img, const int item,
+                                                  const uint32_t chunkFirst, const uint32_t chunkEnd)
 {
   const int W = g.width, H = g.height, hW = W >> 1, hH = H >> 1, spr = W >> 4;
   auto clampc = [&](int x) { return x < 0 ? 0 : (x > W - 1 ? W - 1 : x); };
@@ -470,6 +494,9 @@ __device__ __forceinline__ void lines_sector_item(const Geometry& g, const int2 
     wholeRow = true;
   }
   else
+    return;
+  const uint32_t chunk = (uint32_t)row * (uint32_t)(W >> 3) + 2u * (uint32_t)sec;
+  if (chunk < chunkFirst || chunk >= chunkEnd)
     return;
   uint4* const p = reinterpret_cast<uint4*>(img + (size_t)row * outLine + (size_t)sec * 32);
   const uint4 a = __ldcg(p), b = __ldcg(p + 1);                  // L2: the fused caller reads what other SMs have just written
@@ -545,22 +572,26 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
     {
       const int cnt = numFrames - f0 < chunk ? numFrames - f0 : chunk;
       const dim3 cgrid(igrid.x, (unsigned)(cnt < 65535 ? cnt : 65535));
-      // fused overlays count CTAs in per frame: every frame must be visited by exactly gridDim.x CTAs (it is: the frame
-      // loop strides by gridDim.y for all of them alike) and the frame's record must exist
-      // By default only for long passes (>= 384 MiB of images): the last CTA of a frame walks the frame's ~H * 6 sectors in
-      // H * 6 / 256 dependent rounds, which a short pass cannot hide -- 64 x 320x240: 0.034 ms fused against 0.018 ms with the
-      // sector kernel, 1024 x 320x240 0.132 against 0.130 ms, 4096 x 320x240 0.435 against 0.475 ms, 1024 x 640x480 0.440
-      // against 0.477 ms (profiles/r02w_*, r02x_*).
-      const bool longPass = (unsigned long long)cnt * perFrame >= (384ull << 20);
-      const bool fused = ((g_sectorOverlay < 0 && longPass) || g_sectorOverlay >= 2) && draw != nullptr && (kind == KIND_WL || kind == KIND_OL);
-      // blocks of 256 items per CTA: forced (2: 1, 3: 2, 4: 4, 5: 8 ...) or, by default, as many as leave about four waves of
-      // CTAs, at most 16 -- measured on 1024 x 640x480 WL (profiles/r02w_*): 1 / 2 / 4 / 8 / 16 / 32 / 64 blocks per CTA
-      // 0.564 / 0.490 / 0.466 / 0.449 / 0.438 / 0.447 / 0.464 ms against 0.476 ms with the separate sector kernel
+      // Line sensors: the overlays inside the streaming kernel (one launch fewer, the sectors patched while still in L2).
+      //  * default (-1) and 9..15, CTA-local: a CTA patches the sectors the lines cross among the rows it has just written
+      //    itself, after one barrier.  Paid per CTA, so a CTA takes several blocks of 256 items: 1 / 4 / 8 / 16 / 32 blocks
+      //    0.500 / 0.416 / 0.404 / 0.410 / 0.422 ms per 1024 x 640x480 WL against 0.477 ms with the separate sector kernel,
+      //    OL 0.486 against 0.548 ms, 4096 x 320x240 0.424 against 0.474 ms, 1024 x 320x240 0.123 against 0.130 ms,
+      //    64 x 320x240 (one block per CTA) 0.0172 against 0.0179 ms (profiles/r02z_*): by default up to 8 blocks, as long as
+      //    about four waves of CTAs are left.
+      //  * 2..8, counting: the CTAs of a frame count themselves in at the frame's DrawInfo record (every frame is visited by
+      //    exactly gridDim.x CTAs) and the last one patches the whole frame: 0.438 ms at best for the same 1024 x 640x480 WL
+      //    (16 blocks per CTA), and short passes cannot hide the last CTA's H * 6 / 256 dependent rounds (64 x 320x240: 0.034
+      //    against 0.018 ms; profiles/r02w_*, r02x_*).  Kept for measurements.
+      const bool fused = (g_sectorOverlay < 0 || g_sectorOverlay >= 2) && draw != nullptr && (kind == KIND_WL || kind == KIND_OL);
+      const int fuseLocal = (g_sectorOverlay < 0 || g_sectorOverlay >= 9) ? 1 : 0;
       unsigned fuseIters = 1u;
-      if (g_sectorOverlay >= 2)
-        fuseIters = 1u << (g_sectorOverlay <= 8 ? g_sectorOverlay - 2 : 6);
+      if (g_sectorOverlay >= 9)
+        fuseIters = 1u << (g_sectorOverlay <= 15 ? g_sectorOverlay - 9 : 6);
+      else if (g_sectorOverlay >= 2)
+        fuseIters = 1u << (g_sectorOverlay - 2);
       else
-        while (fuseIters < 16u && (unsigned long long)cgrid.x * cgrid.y / (fuseIters * 2u) >= 4ull * 148ull * 8ull)
+        while (fuseIters < 8u && (unsigned long long)cgrid.x * cgrid.y / (fuseIters * 2u) >= 4ull * 148ull * 8ull)
           fuseIters *= 2u;
       const uint8_t* cf = frames + (size_t)f0 * g.frameStride;
       const FrameParams* cp = params + (size_t)f0 * paramStride;
@@ -570,16 +601,16 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
       uint8_t* cpv = previews + (size_t)f0 * previewStride;
 #define TRIK_PREVIEW_ID(K)                                                                                         \
   preview_identity_kernel<K, false><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,               \
-                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1);     \
+                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1, 0);     \
   preview_overlay_kernel<K><<<(unsigned)cnt, OVERLAY_THREADS, 0, stream>>>(g, cp, paramStride, cd, co, pg, cpv, previewStride)
 #define TRIK_PREVIEW_LINES(K)                                                                                      \
   preview_identity_kernel<K, false><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,               \
-                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1);     \
+                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1, 0);     \
   preview_lines_sector_kernel<K><<<dim3((unsigned)((g.height * 6 + 2 * (g.width >> 4) + 127) / 128), cgrid.y), 128, 0, stream>>>( \
       g, cd, outLine, cpv, previewStride, cnt)
 #define TRIK_PREVIEW_FUSED(K)                                                                                      \
   preview_identity_kernel<K, true><<<dim3((cgrid.x + fuseIters - 1) / fuseIters, cgrid.y), 256, 0, stream>>>(          \
-      g, cf, cp, paramStride, cb, outLine, cpv, previewStride, cnt, cprMagic, colFirst, colLast, const_cast<DrawInfo*>(cd), (int)fuseIters); \
+      g, cf, cp, paramStride, cb, outLine, cpv, previewStride, cnt, cprMagic, colFirst, colLast, const_cast<DrawInfo*>(cd), (int)fuseIters, fuseLocal); \
   --g_launches_preview
       switch (kind)
       {
