@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "trik-media-sensors-dsp_b200", "libtrikb200.so")
 # the instantiations the bench / sweeps actually launch
 WANT = ["vsum_kernelILb0ELi4ELi512E", "vsum16_kernelILi4ELi256ELi4E", "wo_lut_kernelILi4ELb0E", "om_table_kernelE",
-        "om_table_list_kernelE", "om_major_kernelILi4ELi3E", "oo_bitmap_lut_kernelILb0E", "oo_cluster_kernelE"]
+        "om_table_list_kernelE", "om_major_kernelILi4ELi3E", "oo_bitmap_lut_kernelILb0E", "oo_cluster_kernelE",
+        "preview_identity_kernelILi1ELb1E", "preview_identity_kernelILi3ELb1E", "preview_identity_kernelILi1ELb0E"]
 
 
 def main():
