@@ -365,6 +365,9 @@ void trikb200_setPreviewChunkMB(XDAS_Int32 mb);
  * CTA-local with a forced 1, 2 .. 64 blocks per CTA.  All byte-identical (tests/test_preview_gpu.py); measurements in
  * DESIGN.md 3.7 */
 void trikb200_setPreviewSectorOverlay(XDAS_Int32 on);
+/* tuning knob: 1 (default) = the 1:1 preview of a webcam object sensor batch that went through the chroma table of its one
+ * threshold set detects through that table too (two byte look-ups per pixel pair), 0 = always the HSV arithmetic */
+void trikb200_setPreviewTable(XDAS_Int32 on);
 /* tuning knob: edge-line kernel, 0 = packed four-pixels-per-thread form (default, needs 4-byte aligned rows), 1 = one thread
  * per column (first version) */
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant);

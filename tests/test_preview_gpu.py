@@ -199,3 +199,41 @@ def test_long_preview_pass_default_route(kind):
         assert got[(-1, rep)][1] == got[(1, rep)][1], (kind, rep)
         assert torch.equal(got[(-1, rep)][0], got[(1, rep)][0]), (kind, rep)
         assert got[(-1, rep)][2] == got[(1, rep)][2] - 1, (kind, rep, got[(-1, rep)][2], got[(1, rep)][2])
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("size", [(320, 240), (640, 480)])
+def test_wo_preview_through_the_chroma_table(size, variant):
+    """webcam object sensor, 1:1 preview of a batch that goes through the chroma table of its one threshold set: the preview
+    pass detects through the same table (two byte look-ups per pixel pair, the luma masks for ragged entries) instead of the
+    HSV arithmetic -- every preview byte and every record equal to the arithmetic route (trikb200_setPreviewTable(0) and the
+    arithmetic main pass) and to single process() calls, which test_preview_matches_reference pins to the reference"""
+    w, h = size
+    n = 41
+    fams = ["scene", "noise", "halves", "bluewrap", "blobs"]
+    frames = np.stack([synth.make_frame(fams[s % 5], s, w, h, "yuyv") for s in range(n)])
+    ia = xdm.RangeInArgsAlg(*args_for("wo", variant))
+    L = sensors.lib()
+    got = {}
+    try:
+        for name, lut, pvt in (("table", 1, 1), ("table_main_only", 1, 0), ("arith", -1, 1)):
+            L.trikb200_setLutMode(lut)
+            L.trikb200_setPreviewTable(pvt)
+            codec = open_sensor("wo", w, h, out_w=w, out_h=h)
+            prev = np.full((n, w * h * 2), 0xAB, dtype=np.uint8)
+            ret, outs = codec.process_batch(frames, ia, previews=prev)
+            assert ret == 0, sensors.last_error()
+            got[name] = (prev, [bytes(memoryview(o)) for o in outs])
+            codec.close()
+    finally:
+        L.trikb200_setLutMode(0)
+        L.trikb200_setPreviewTable(1)
+    for name in ("table", "table_main_only"):
+        assert got[name][1] == got["arith"][1], name
+        assert np.array_equal(got[name][0], got["arith"][0]), (name, size, variant)
+    assert (got["table"][0].reshape(n, -1, 2) == np.array([0xE0, 0xFF], dtype=np.uint8)).all(axis=2).any(), "nothing detected at all"
+    codec = open_sensor("wo", w, h, out_w=w, out_h=h)
+    for i in range(0, n, 5):
+        r, oa = codec.process(frames[i], ia)
+        assert r == 0 and np.array_equal(codec.preview[:w * h * 2], got["table"][0][i]), (size, variant, i)
+    codec.close()

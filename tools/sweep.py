@@ -36,6 +36,7 @@ def main():
     sensors.lib().trikb200_setLutSkew(int(os.environ.get("SKEW", "1")))
     sensors.lib().trikb200_setPreviewChunkMB(int(os.environ.get("PVCHUNK", "0")))   # MiB of preview images per sub-batch, 0 = all at once
     sensors.lib().trikb200_setPreviewSectorOverlay(int(os.environ.get("PVSECTOR", "-1")))   # -1: fused into the streaming kernel (default), 0: generic overlay kernel, 1: sector kernel
+    sensors.lib().trikb200_setPreviewTable(int(os.environ.get("PVLUT", "1")))       # 0: WO preview detects by arithmetic even when the batch has its table
     sensors.lib().trikb200_setLutParts(int(os.environ.get("LUTPARTS", "0")))        # bands per frame of the WO table kernel
     sensors.lib().trikb200_setOverlapLaunch(int(os.environ.get("OVERLAP", "1")))   # 0: no programmatic dependent launches
     peak = 6541.1

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libtrikb200.so")
 STAMP = os.path.join(HERE, ".libtrikb200.stamp")
 
 SOURCES = ["trik_kernels.cu", "trik_kernels_line.cu", "trik_kernels_lut.cu", "trik_kernels_anneal.cu", "trik_kernels_grid.cu", "trik_kernels_omtab.cu", "trik_kernels_ommaj.cu", "trik_kernels_ingest.cu", "trik_kernels_edge.cu", "trik_kernels_detect.cu", "trik_kernels_preview.cu", "trik_capi.cu", "trik_host.cpp"]
-HEADERS = ["trik_kernels.cuh", "trik_pixel.cuh", "trik_line.cuh", "trik_host.hpp"]
+HEADERS = ["trik_kernels.cuh", "trik_pixel.cuh", "trik_line.cuh", "trik_lut.cuh", "trik_host.hpp"]
 KINDS = ("wo", "wl", "oo", "ol", "om")
 
 NVCC_FLAGS = [

@@ -817,6 +817,8 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
     dOut = in->dOut;
   }
   const int pstride = broadcast ? 0 : 1;
+  const uint8_t* pvLutTable = nullptr;
+  const uint32_t* pvLutMasks = nullptr;
   switch (kind)
   {
     case KIND_WO: case KIND_WL: case KIND_OL:
@@ -824,6 +826,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       // WO batches that share one threshold set go through the chroma table (built once per set, kept with the
       // handle); below ~256 frames building it costs more than it saves unless it is already there
       bool useLut = false;
+      pvLutTable = nullptr; pvLutMasks = nullptr;
       if (kind == KIND_WO && broadcast && g_lutMode >= 0 && g.width % 8 == 0)
       {
         const FrameParams& fp = in->paramsScratch[0];
@@ -884,6 +887,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       }
       else if (useLut)
       {
+        pvLutTable = in->dLutTable; pvLutMasks = in->dLutMasks;   // the preview pass of this batch detects through it too
         if (!in->grow_device(in->dAcc, in->dAccCap, (size_t)b.n, true)) return false;
         CUDA_TRY(launch_wo_lut(g, b.n, dFrames, in->dParams, in->dLutTable, in->dLutMasks,
                                reinterpret_cast<TargetOut*>(dOut), in->smCount, s, in->dAcc));
@@ -1081,7 +1085,7 @@ bool enqueue_batch(Instance* in, const BatchView& b, Pending& pend)
       CUDA_TRY(cudaMemset2DAsync(dPrev, (size_t)pstrideBytes, 0, previewBytes, b.n, s));
     CUDA_TRY(launch_preview(kind, g, b.n, dFrames, in->dParams, pstride, in->dBitmaps, in->dDraw,
                             reinterpret_cast<const int32_t*>(dOut), in->outWidth, in->outHeight, in->outLineLength,
-                            in->dLastRow, in->dLastCol, in->dHi2ho, in->dWi2wo, dPrev, pstrideBytes, s));
+                            in->dLastRow, in->dLastCol, in->dHi2ho, in->dWi2wo, dPrev, pstrideBytes, s, pvLutTable, pvLutMasks));
     if (previewInPlace)
       CUDA_TRY(cudaMemcpyAsync(in->hPreview, dPrev, previewBytes * b.n, cudaMemcpyDeviceToHost, s));
     else if (!b.previewsOnDevice)
@@ -1935,6 +1939,7 @@ void trikb200_setLutSkew(XDAS_Int32 on) { set_lut_skew(on); }
 void trikb200_setLutParts(XDAS_Int32 parts) { set_lut_parts(parts); }
 void trikb200_setPreviewChunkMB(XDAS_Int32 mb) { set_preview_chunk_bytes((long long)mb << 20); }
 void trikb200_setPreviewSectorOverlay(XDAS_Int32 on) { set_preview_sector_overlay(on); }
+void trikb200_setPreviewTable(XDAS_Int32 on) { set_preview_table(on); }
 void trikb200_setEdgeLineVariant(XDAS_Int32 variant) { set_edge_variant(variant); }
 void trikb200_setMxnTableThreads(XDAS_Int32 threads) { set_om_table_threads(threads); }
 void trikb200_setZeroCopyBytes(XDAS_Int32 bytes) { g_zeroCopyBytes = bytes; }

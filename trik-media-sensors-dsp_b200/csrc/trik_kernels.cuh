@@ -95,7 +95,7 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
                            int paramStride, const uint16_t* bitmaps, const DrawInfo* draw, const int32_t* omColours,
                            int outW, int outH, int outLine, const int32_t* lastRow, const int32_t* lastCol,
                            const int32_t* hi2ho, const int32_t* wi2wo, uint8_t* previews, long long previewStride,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const uint8_t* lutTable = nullptr, const uint32_t* lutMasks = nullptr);
 
 // exhaustive pixel-function probes for the parity tests: out[i] for i = blockIdx*blockDim+threadIdx
 cudaError_t launch_probe_yuv2rgb(uint32_t first, uint32_t count, uint32_t* out, cudaStream_t stream);
@@ -125,6 +125,7 @@ cudaError_t launch_wo_lut(const Geometry& g, int numFrames, const uint8_t* frame
 void set_lut_parts(int parts);
 void set_preview_chunk_bytes(long long bytes);
 void set_preview_sector_overlay(int on);
+void set_preview_table(int on);
 // the same for a batch under several threshold sets, in one launch: set k has count[k] frames, their indices at
 // frameList + listOffset[k], its FrameParams at params[paramIndex[k]] and its table / masks; the launcher fills the rest
 constexpr int LUT_MAX_SETS = 8;

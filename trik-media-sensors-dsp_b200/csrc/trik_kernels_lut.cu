@@ -28,6 +28,7 @@
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
 #include "trik_line.cuh"
+#include "trik_lut.cuh"
 
 namespace trikb200 {
 
@@ -36,13 +37,6 @@ static int g_lutSkew = 1;
 void set_lut_skew(int on) { g_lutSkew = on; }
 static int g_lutParts = 0;                    // bands per frame of the WO table kernel: 0 = chosen per launch, 1 / 2 / 4 / 8 = fixed
 void set_lut_parts(int parts) { g_lutParts = parts; }
-
-// (lo, nhi = 255 - hi) codes with lo > hi: no luma satisfies lo <= Y <= hi, so the interval test fails by itself
-constexpr uint32_t LUT_NEVER_LO = 255u, LUT_NEVER_NHI = 255u;        // hi = 0
-constexpr uint32_t LUT_RAGGED_LO = 255u, LUT_RAGGED_NHI = 254u;      // hi = 1: marks "consult the mask"
-constexpr uint32_t LUT_RAGGED_CODE = LUT_RAGGED_LO * 256u + LUT_RAGGED_NHI;     // lo * 256 + nhi
-constexpr uint32_t LUT_STRIDE_PLAIN = 65536u, LUT_STRIDE_SKEW = 66560u;
-constexpr uint32_t LUT_SKEW_IMAGE_OFS = 2u * LUT_STRIDE_PLAIN;                  // second image inside the table buffer
 
 // ---------------------------------------------------------------------------------------------
 // table construction: one warp per chroma pair
@@ -122,28 +116,6 @@ cudaError_t launch_chroma_table(uint32_t from, uint32_t to, uint32_t expected, u
 __device__ __forceinline__ void group_barrier(int id, int count)
 {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory");
-}
-
-// Pass bits of a YUYV pixel pair (bit 15: pixel 0, bit 31: pixel 1) from its table entry: pass <=> lo <= Y <= hi.
-// Guard bit 15 in every 16-bit lane keeps the two subtractions of one 32-bit operation apart (0x8000 + a - b with
-// bytes a, b never borrows) and doubles as the result: it stays set <=> a >= b.  Y <= hi is tested as
-// 255 - Y >= 255 - hi, so that both compares are one IMAD each (lane replication by 0x10001 included).
-__device__ __forceinline__ uint32_t lut_pass_pair(uint32_t word, uint32_t lo, uint32_t nhi)
-{
-  const uint32_t yG  = (word & 0x00FF00FFu) | 0x80008000u;             // 0x8000 + Y per lane
-  const uint32_t nyG = (~word & 0x00FF00FFu) | 0x80008000u;            // 0x8000 + 255 - Y per lane
-  const uint32_t geLo = yG - lo * 0x00010001u;
-  const uint32_t leHi = nyG - nhi * 0x00010001u;
-  return geLo & leHi & 0x80008000u;
-}
-
-// pass bits of a pair whose entry is RAGGED: the luma masks decide
-__device__ __forceinline__ uint32_t lut_pass_pair_masks(uint32_t word, uint32_t ci, const uint32_t* __restrict__ masks)
-{
-  const uint32_t y0 = word & 0xFFu, y1 = (word >> 16) & 0xFFu;
-  const uint32_t m0 = __ldg(masks + (size_t)ci * 8u + (y0 >> 5));
-  const uint32_t m1 = __ldg(masks + (size_t)ci * 8u + (y1 >> 5));
-  return (((m0 >> (y0 & 31u)) & 1u) << 15) | (((m1 >> (y1 & 31u)) & 1u) << 31);
 }
 
 // Persistent CTA: `groups` independent groups of `gthreads` threads, one frame per group at a time.

@@ -18,6 +18,7 @@
 #include <atomic>
 #include "trik_kernels.cuh"
 #include "trik_pixel.cuh"
+#include "trik_lut.cuh"
 
 namespace trikb200 {
 
@@ -29,6 +30,8 @@ static int g_sectorOverlay = -1;                         // line sensors, 1:1 pr
                                                          // kernel, CTA-local (default); 0 = generic overlay kernel; 1 = full-sector kernel;
                                                          // 2..8 = inside, counting (forced blocks per CTA); 9..15 = inside, CTA-local (forced)
 void set_preview_sector_overlay(int on) { g_sectorOverlay = on; }
+static int g_previewTable = 1;                           // WO, 1:1 preview: detection through the batch's chroma table when there is one
+void set_preview_table(int on) { g_previewTable = on; }
 
 __device__ __forceinline__ uint16_t rgb565x(uint32_t rgb888)           // writeOutputPixel (:66-70)
 {
@@ -152,7 +155,8 @@ __global__ void __launch_bounds__(256)
 preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, const FrameParams* __restrict__ params,
                         const int paramStride, const uint16_t* __restrict__ bitmaps, const int outLine,
                         uint8_t* __restrict__ previews, const long long previewStride, const int numFrames,
-                        const uint32_t cprMagic, const int colFirst, const int colLast, DrawInfo* draw, const int iters, const int local)
+                        const uint32_t cprMagic, const int colFirst, const int colLast, DrawInfo* draw, const int iters, const int local,
+                        const uint8_t* __restrict__ lutTable, const uint32_t* __restrict__ lutMasks)
 {
   constexpr bool PLANAR = (KIND == KIND_OO || KIND == KIND_OL || KIND == KIND_OM);
   __shared__ uint16_t s_lut43[256];
@@ -244,7 +248,17 @@ preview_identity_kernel(const Geometry g, const uint8_t* __restrict__ frames, co
       const uint32_t cb = __vminu2(__vmaxu2(kb, 0x80008000u), 0xBFFFBFFFu);
       const uint32_t rgb = (__umulhi(cr, 1u << 23) & 0x001F001Fu) | (__umulhi(cg, 1u << 29) & 0x07E007E0u) | ((cb * 4u) & 0xF800F800u);
       uint32_t keep = 0xFFFFFFFFu;                               // 0xFFFF in the lanes that keep their own colour
-      if (KIND == KIND_WO)
+      if (KIND == KIND_WO && lutTable)
+      {
+        // the batch's threshold set has its chroma table (the one the main pass has just used, trik_kernels_lut.cu): two
+        // byte look-ups (L1 / L2) and two packed compares instead of the HSV arithmetic; ragged entries ask the luma masks
+        const uint32_t ci = __byte_perm(cw[j], 0u, 0x4431);     // U | V << 8
+        const uint32_t lo = __ldg(lutTable + ci), nhi = __ldg(lutTable + LUT_STRIDE_PLAIN + ci);
+        const uint32_t bits = (lo * 256u + nhi == LUT_RAGGED_CODE) ? lut_pass_pair_masks(cw[j], ci, lutMasks)
+                                                                   : lut_pass_pair(cw[j], lo, nhi);
+        keep = ~(((bits >> 15) & 0x00010001u) * 0xFFFFu);
+      }
+      else if (KIND == KIND_WO)
       {
         // the pair-wise threshold of the sum kernel (V, then S, then hue, each with a warp-wide early out)
         const uint32_t det = detect_pair_bits(yy[j], cw[j], coef, s_lutHue, s_lut255, bd, expected);
@@ -533,8 +547,11 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
                            int paramStride, const uint16_t* bitmaps, const DrawInfo* draw, const int32_t* omColours,
                            int outW, int outH, int outLine, const int32_t* lastRow, const int32_t* lastCol,
                            const int32_t* hi2ho, const int32_t* wi2wo, uint8_t* previews, long long previewStride,
-                           cudaStream_t stream)
+                           cudaStream_t stream, const uint8_t* lutTable, const uint32_t* lutMasks)
 {
+  // WO: the chroma table of the batch's ONE threshold set, when the main pass went through it (else NULL: arithmetic)
+  const uint8_t* pvTable = (kind == KIND_WO && g_previewTable) ? lutTable : nullptr;
+  const uint32_t* pvMasks = pvTable ? lutMasks : nullptr;
   if (numFrames <= 0 || outW <= 0 || outH <= 0)
     return cudaSuccess;
   PreviewGeom pg{outW, outH, outLine, lastRow, lastCol, hi2ho, wi2wo};
@@ -601,16 +618,16 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
       uint8_t* cpv = previews + (size_t)f0 * previewStride;
 #define TRIK_PREVIEW_ID(K)                                                                                         \
   preview_identity_kernel<K, false><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,               \
-                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1, 0);     \
+                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1, 0, pvTable, pvMasks);     \
   preview_overlay_kernel<K><<<(unsigned)cnt, OVERLAY_THREADS, 0, stream>>>(g, cp, paramStride, cd, co, pg, cpv, previewStride)
 #define TRIK_PREVIEW_LINES(K)                                                                                      \
   preview_identity_kernel<K, false><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,               \
-                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1, 0);     \
+                                                        previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1, 0, pvTable, pvMasks);     \
   preview_lines_sector_kernel<K><<<dim3((unsigned)((g.height * 6 + 2 * (g.width >> 4) + 127) / 128), cgrid.y), 128, 0, stream>>>( \
       g, cd, outLine, cpv, previewStride, cnt)
 #define TRIK_PREVIEW_FUSED(K)                                                                                      \
   preview_identity_kernel<K, true><<<dim3((cgrid.x + fuseIters - 1) / fuseIters, cgrid.y), 256, 0, stream>>>(          \
-      g, cf, cp, paramStride, cb, outLine, cpv, previewStride, cnt, cprMagic, colFirst, colLast, const_cast<DrawInfo*>(cd), (int)fuseIters, fuseLocal); \
+      g, cf, cp, paramStride, cb, outLine, cpv, previewStride, cnt, cprMagic, colFirst, colLast, const_cast<DrawInfo*>(cd), (int)fuseIters, fuseLocal, nullptr, nullptr); \
   --g_launches_preview
       switch (kind)
       {

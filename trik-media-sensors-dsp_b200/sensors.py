@@ -58,6 +58,7 @@ def lib():
         l.trikb200_setLutParts.argtypes = [C.c_int32]
         l.trikb200_setPreviewChunkMB.argtypes = [C.c_int32]
         l.trikb200_setPreviewSectorOverlay.argtypes = [C.c_int32]
+        l.trikb200_setPreviewTable.argtypes = [C.c_int32]
         l.trikb200_setEdgeLineVariant.argtypes = [C.c_int32]
         l.trikb200_setMxnTableThreads.argtypes = [C.c_int32]
         l.trikb200_setZeroCopyBytes.argtypes = [C.c_int32]
