@@ -616,6 +616,7 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
       const DrawInfo* cd = draw ? draw + f0 : nullptr;
       const int32_t* co = omColours ? omColours + (size_t)f0 * 100 : nullptr;
       uint8_t* cpv = previews + (size_t)f0 * previewStride;
+      int launched = 2;                                          // base layer + overlays; one when the overlays are inside
 #define TRIK_PREVIEW_ID(K)                                                                                         \
   preview_identity_kernel<K, false><<<cgrid, 256, 0, stream>>>(g, cf, cp, paramStride, cb, outLine, cpv,               \
                                                         previewStride, cnt, cprMagic, colFirst, colLast, nullptr, 1, 0, pvTable, pvMasks);     \
@@ -628,7 +629,7 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
 #define TRIK_PREVIEW_FUSED(K)                                                                                      \
   preview_identity_kernel<K, true><<<dim3((cgrid.x + fuseIters - 1) / fuseIters, cgrid.y), 256, 0, stream>>>(          \
       g, cf, cp, paramStride, cb, outLine, cpv, previewStride, cnt, cprMagic, colFirst, colLast, const_cast<DrawInfo*>(cd), (int)fuseIters, fuseLocal, nullptr, nullptr); \
-  --g_launches_preview
+  launched = 1
       switch (kind)
       {
         case KIND_WO: TRIK_PREVIEW_ID(KIND_WO); break;
@@ -641,7 +642,7 @@ cudaError_t launch_preview(int kind, const Geometry& g, int numFrames, const uin
 #undef TRIK_PREVIEW_FUSED
 #undef TRIK_PREVIEW_LINES
 #undef TRIK_PREVIEW_ID
-      g_launches_preview += 2;
+      g_launches_preview += launched;
     }
     return cudaGetLastError();
   }
